@@ -398,12 +398,17 @@ static long isoform_fragments(const orc *o, const unsigned char *state, char typ
     int m = 0, ns = 1;
     sums[0] = 0.f;
     long n = 0;
-    for (int step = 0; step < L - 1; step++) {
+    /* A one-residue peptide is the one case where the walk starts ON the last residue: the
+     * reference's end test (isFragmentEnd: last residue AND no neutral-loss variant left,
+     * cpp/ModifiedPeptide.cpp:516-524) then lets every variant but the last one through. */
+    int steps = (L == 1) ? 1 : L - 1;
+    for (int step = 0; step < steps; step++) {
         int i = fwd ? step : L - 1 - step;
         int s = state[i];
         run = (step == 0) ? o->res[i][s] : (o->res[i][s] + run);
         if (o->nl[i][s] != 0.f) { stack[m++] = o->nl[i][s]; ns = power_set_sums(stack, m, sums); }
-        for (int v = 0; v < ns; v++) {
+        int emit = (L == 1) ? ns - 1 : ns;
+        for (int v = 0; v < emit; v++) {
             if (n < cap) out[n] = fragment_mz(run, sums[v], type, z);
             n++;
         }

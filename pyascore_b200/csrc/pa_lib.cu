@@ -1,0 +1,1003 @@
+// libpyascore_b200: host orchestration + C ABI (include/pyascore_b200.h).
+//
+// One scorer = one GPU.  A batch is cut into chunks of PSMs (and the spectra they reference);
+// chunks alternate between two CUDA streams so that the H2D copy and binning of chunk c+1
+// overlap the scoring of chunk c.  The only host<->device synchronisation inside a chunk is
+// the read-back of the plan totals (number of isoforms / work units), which sizes the scratch.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "pa_kernels.cuh"
+
+#define PA_VERSION 100
+#define PA_CHUNK_PSM 131072
+#define PA_CHUNK_PEAKS (96ll << 20)     // peaks per chunk (1.5 GB of float64 pairs)
+#define PA_TABLE_MIN 512
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct PlanTotals {          // device -> host after planning a chunk
+    unsigned long long combo_bits[64];
+    int max_frag, max_list;
+    long long total_iso;
+    int total_units;
+    int pad;
+};
+
+struct Slot {                // per-stream working set
+    cudaStream_t st = nullptr;
+    // staged inputs
+    DevBuf spec_off, mz, inten, psm_spec, pep_off, pep, n_mod, max_charge, aux_off, aux_pos, aux_mass, mod_off;
+    // K1
+    DevBuf rmz, rrank, rcount, g_bin, g_tmp;
+    // plan
+    DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
+    // K2/K3
+    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups;
+    // staged outputs
+    DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
+    PlanTotals* h_totals = nullptr;      // pinned
+    unsigned long long* h_lookups = nullptr;
+    cudaEvent_t ev_plan = nullptr;
+    void release() {
+        DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
+                         &aux_mass, &mod_off, &rmz, &rrank, &rcount, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
+                         &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
+                         &iso_w, &g_sort, &g_lists, &lookups, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &o_status};
+        for (DevBuf* b : all) b->release();
+        if (h_totals) cudaFreeHost(h_totals);
+        if (h_lookups) cudaFreeHost(h_lookups);
+        if (ev_plan) cudaEventDestroy(ev_plan);
+        if (st) cudaStreamDestroy(st);
+        h_totals = nullptr; h_lookups = nullptr; ev_plan = nullptr; st = nullptr;
+    }
+};
+
+struct ChunkView {           // device-side views of the chunk in flight (kept for fetch calls)
+    PaBatchDev b;
+    int64_t n_psm = 0, psm_lo = 0;
+    const int64_t* iso_off = nullptr;
+    const int32_t* psm_S = nullptr;
+    const int32_t* psm_status = nullptr;
+    PaIso iso;
+    int max_list = 0;
+    bool valid = false;
+    int slot = 0;
+};
+
+}  // namespace
+
+struct pa_scorer {
+    int device = 0;
+    int sm_count = 148;
+    std::string mod_group, frag_types;
+    float bin_size = 100.f, mod_mass = 0.f, err = 0.5f;
+    int n_top = PA_N_TOP;
+    float nl_mass[256];
+    bool nl_has[256];
+    std::vector<float> nl_values;          // distinct non-zero loss masses, index+1 = device index
+    bool nl_dirty = true;
+    PaCfg cfg;
+    DevBuf d_T, d_logd, d_binom, d_nl_sums, d_nl_nvar, d_perm_pool, d_perm_off;
+    int table_n = -1;
+    float lps[PA_N_TOP], lpf[PA_N_TOP];
+    std::vector<int64_t> perm_off;         // [64*64]
+    std::vector<uint32_t> perm_pool;
+    bool perm_dirty = true;
+    Slot slot[2];
+    ChunkView kept;
+    pa_counters_t ctr;
+    std::string error;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    int attr_set = 0;
+};
+
+static int fail(pa_scorer* s, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (s) s->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(s, PA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// cpp/Types.h:7-30
+static float residue_mass_host(char c) {
+    switch (c) {
+        case 'G': return 57.02146f;  case 'A': return 71.03711f;  case 'S': return 87.03203f;
+        case 'P': return 97.05276f;  case 'V': return 99.06841f;  case 'T': return 101.04768f;
+        case 'C': return 103.00919f; case 'L': return 113.08406f; case 'I': return 113.08406f;
+        case 'N': return 114.04293f; case 'D': return 115.02694f; case 'Q': return 128.05858f;
+        case 'K': return 128.09496f; case 'E': return 129.04259f; case 'M': return 131.04049f;
+        case 'H': return 137.05891f; case 'F': return 147.06841f; case 'U': return 150.95364f;
+        case 'R': return 156.10111f; case 'Y': return 163.06333f; case 'W': return 186.07931f;
+        case 'O': return 237.14773f;
+    }
+    return NAN;
+}
+
+// ---- neutral-loss variant table -----------------------------------------------------------------
+// State = capped multiplicity (0,1,2) of each distinct loss mass on the stack, 2 bits per mass.
+// For every state: PowerSetSum(stack, 2) of cpp/Util.cpp:89-160 -- sums of <=2 stack elements in
+// float32, sorted ascending, de-duplicated by exact equality.  Float addition commutes, so the
+// multiset fixes the result.
+static void build_nl_tables(const std::vector<float>& vals, std::vector<float>& sums, std::vector<uint8_t>& nvar,
+                            int& nvar_cap) {
+    sums.assign(256 * 16, 0.f);
+    nvar.assign(256, 1);
+    nvar_cap = 1;
+    int g = (int)vals.size();
+    for (int st = 0; st < 256; st++) {
+        int cnt[4];
+        bool ok = true;
+        for (int v = 0; v < 4; v++) { cnt[v] = (st >> (2 * v)) & 3; if (cnt[v] == 3 || (v >= g && cnt[v])) ok = false; }
+        if (!ok) continue;
+        std::vector<float> stack;
+        for (int v = 0; v < g; v++) for (int c = 0; c < cnt[v]; c++) stack.push_back(vals[v]);
+        std::vector<float> out;
+        out.push_back(0.f);
+        for (size_t i = 0; i < stack.size(); i++) {
+            float s1 = 0.f + stack[i];
+            out.push_back(s1);
+            if (stack.size() >= 2) for (size_t j = i + 1; j < stack.size(); j++) out.push_back(s1 + stack[j]);
+        }
+        std::sort(out.begin(), out.end());
+        out.erase(std::unique(out.begin(), out.end()), out.end());
+        if (out.size() > 16) out.resize(16);   // cannot happen for g <= 4 (1 + 4 + 10 = 15)
+        nvar[st] = (uint8_t)out.size();
+        for (size_t i = 0; i < out.size(); i++) sums[st * 16 + i] = out[i];
+        nvar_cap = std::max(nvar_cap, (int)out.size());
+    }
+}
+
+static int refresh_config(pa_scorer* s) {
+    PaCfg& c = s->cfg;
+    c.bin_size = s->bin_size; c.mod_mass = s->mod_mass; c.err = s->err; c.n_top = s->n_top;
+    c.mod_letters = 0; c.allow_n = 0; c.allow_c = 0;
+    for (char ch : s->mod_group) {
+        if (ch >= 'A' && ch <= 'Z') c.mod_letters |= 1u << (ch - 'A');
+        if (ch == 'n') c.allow_n = 1;
+        if (ch == 'c') c.allow_c = 1;
+    }
+    c.n_types = (int)s->frag_types.size();
+    memset(c.types, 0, sizeof(c.types));
+    memcpy(c.types, s->frag_types.data(), s->frag_types.size());
+    for (int i = 0; i < 26; i++) c.res_mass[i] = residue_mass_host((char)('A' + i));
+    // cpp/Ascore.cpp:15-19
+    const float w0[PA_N_TOP] = {0.5f, 0.75f, 1.0f, 1.0f, 1.0f, 1.0f, 0.75f, 0.5f, 0.25f, 0.25f};
+    double sum = 0.;
+    for (float w : w0) sum += w;
+    float fsum = (float)sum;
+    for (int i = 0; i < PA_N_TOP; i++) c.weights[i] = w0[i] / fsum;
+    c.err_gt_half = s->err > 0.5f;
+    if (s->nl_dirty) {
+        s->nl_values.clear();
+        memset(c.nl_upper, 0, sizeof(c.nl_upper));
+        memset(c.nl_lower, 0, sizeof(c.nl_lower));
+        for (int ch = 0; ch < 256; ch++) {
+            if (!s->nl_has[ch] || s->nl_mass[ch] == 0.f) continue;
+            float m = s->nl_mass[ch];
+            int idx = -1;
+            for (size_t v = 0; v < s->nl_values.size(); v++) if (s->nl_values[v] == m) idx = (int)v;
+            if (idx < 0) {
+                if (s->nl_values.size() >= PA_MAX_NL_MASSES)
+                    return fail(s, PA_ERR_UNSUPPORTED, "more than %d distinct neutral-loss masses", PA_MAX_NL_MASSES);
+                s->nl_values.push_back(m);
+                idx = (int)s->nl_values.size() - 1;
+            }
+            if (ch >= 'A' && ch <= 'Z') c.nl_upper[ch - 'A'] = (uint8_t)(idx + 1);
+            if (ch >= 'a' && ch <= 'z') c.nl_lower[ch - 'a'] = (uint8_t)(idx + 1);
+        }
+        c.has_nl = !s->nl_values.empty();
+        std::vector<float> sums; std::vector<uint8_t> nvar;
+        build_nl_tables(s->nl_values, sums, nvar, c.nvar_cap);
+        CK(s->d_nl_sums.ensure(sums.size() * sizeof(float)));
+        CK(s->d_nl_nvar.ensure(nvar.size()));
+        CK(cudaMemcpy(s->d_nl_sums.p, sums.data(), sums.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->d_nl_nvar.p, nvar.data(), nvar.size(), cudaMemcpyHostToDevice));
+        s->nl_dirty = false;
+    }
+    c.nl_sums = s->d_nl_sums.as<float>();
+    c.nl_nvar = s->d_nl_nvar.as<uint8_t>();
+    c.binom = s->d_binom.as<uint32_t>();
+    c.T = s->d_T.as<float>();
+    c.table_n = s->table_n;
+    return PA_OK;
+}
+
+// Score table rows 0..n_max (grown geometrically).  cpp/Ascore.cpp:23-36: p_d = 2*err*d/100.
+static int ensure_table(pa_scorer* s, int n_max) {
+    if (n_max <= s->table_n) return PA_OK;
+    int want = std::max(PA_TABLE_MIN, s->table_n);
+    while (want < n_max) want *= 2;
+    want = std::min(want, (int)PA_MAX_FRAGMENTS);
+    if (want < n_max) return fail(s, PA_ERR_UNSUPPORTED, "score table beyond %d trials", PA_MAX_FRAGMENTS);
+    CK(cudaDeviceSynchronize());
+    size_t entries = ((size_t)want + 1) * ((size_t)want + 2) / 2;
+    DevBuf nt;
+    CK(nt.ensure(entries * PA_N_TOP * sizeof(float)));
+    std::vector<double> logd(want + 2);
+    logd[0] = 0.;
+    for (int m = 1; m <= want + 1; m++) logd[m] = std::log((double)m);
+    CK(s->d_logd.ensure(logd.size() * sizeof(double)));
+    CK(cudaMemcpy(s->d_logd.p, logd.data(), logd.size() * sizeof(double), cudaMemcpyHostToDevice));
+    PaTailArgs a;
+    a.T = nt.as<float>();
+    a.logd = s->d_logd.as<double>();
+    for (int d = 0; d < PA_N_TOP; d++) { a.lps[d] = s->lps[d]; a.lpf[d] = s->lpf[d]; }
+    volatile double one = 1.0;
+    a.log10e = std::log10(std::exp(one));      // cpp/Util.cpp:82
+    int n0 = 0;
+    if (s->table_n >= 0) {                     // keep the rows already built
+        size_t old_entries = ((size_t)s->table_n + 1) * ((size_t)s->table_n + 2) / 2;
+        CK(cudaMemcpy(nt.p, s->d_T.p, old_entries * PA_N_TOP * sizeof(float), cudaMemcpyDeviceToDevice));
+        n0 = s->table_n + 1;
+    }
+    int rows = want - n0 + 1;
+    k_tail_table<<<rows, 128, (want + 2) * sizeof(float)>>>(a, n0, want);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    s->d_T.release();
+    s->d_T = nt;
+    s->table_n = want;
+    s->cfg.T = s->d_T.as<float>();
+    s->cfg.table_n = want;
+    return PA_OK;
+}
+
+// ---- reference tie order ----------------------------------------------------------------------
+// cpp/Ascore.cpp:54,113-120: isoforms come out of a std::unordered_map<long, ScoreContainer> that
+// was filled in the first fragment graph's enumeration order.  We run the very same container
+// (same libstdc++) on the same keys and record, for each hash-iteration position, the isoform's
+// lexicographic rank.  One list per (sites, mods); cached for the life of the scorer.
+static int ensure_perm(pa_scorer* s, int S, int k) {
+    if (s->perm_off[S * 64 + k] >= 0) return PA_OK;
+    const bool fwd = (s->frag_types[0] == 'b' || s->frag_types[0] == 'c');
+    std::vector<int> c(k);
+    for (int i = 0; i < k; i++) c[i] = i;
+    // binomials for ranking
+    std::vector<std::vector<unsigned long long>> C(65, std::vector<unsigned long long>(65, 0));
+    for (int n = 0; n <= 64; n++) { C[n][0] = 1; for (int j = 1; j <= n; j++) C[n][j] = std::min<unsigned long long>(C[n - 1][j - 1] + (j <= n - 1 ? C[n - 1][j] : 0), 1ull << 62); }
+    std::unordered_map<long, uint32_t> m;
+    for (;;) {
+        long key = 0;
+        unsigned long long bits = 0;
+        for (int i = 0; i < k; i++) {
+            int site = fwd ? c[i] : S - 1 - c[i];
+            key |= 1l << (S - 1 - site);
+            bits |= 1ull << site;
+        }
+        // lexicographic rank of the site set (N->C)
+        unsigned long long r = 0;
+        int prev = -1, i = 0;
+        for (int site = 0; site < S; site++)
+            if ((bits >> site) & 1ull) {
+                for (int j = prev + 1; j < site; j++) r += C[S - 1 - j][k - 1 - i];
+                prev = site; i++;
+            }
+        m[key] = (uint32_t)r;
+        int q = k - 1;
+        while (q >= 0 && c[q] == S - k + q) q--;
+        if (q < 0) break;
+        c[q]++;
+        for (int j = q + 1; j < k; j++) c[j] = c[j - 1] + 1;
+    }
+    s->perm_off[S * 64 + k] = (int64_t)s->perm_pool.size();
+    for (auto& kv : m) s->perm_pool.push_back(kv.second);
+    s->perm_dirty = true;
+    return PA_OK;
+}
+
+static int upload_perms(pa_scorer* s) {
+    if (!s->perm_dirty) return PA_OK;
+    CK(cudaDeviceSynchronize());
+    CK(s->d_perm_pool.ensure(std::max<size_t>(s->perm_pool.size(), 1) * sizeof(uint32_t)));
+    CK(s->d_perm_off.ensure(s->perm_off.size() * sizeof(int64_t)));
+    if (!s->perm_pool.empty())
+        CK(cudaMemcpy(s->d_perm_pool.p, s->perm_pool.data(), s->perm_pool.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_perm_off.p, s->perm_off.data(), s->perm_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    s->perm_dirty = false;
+    return PA_OK;
+}
+
+static cudaEvent_t next_event(pa_scorer* s) {
+    if (s->ev_used == s->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s->ev_pool.push_back(e);
+    }
+    return s->ev_pool[s->ev_used++];
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int pa_version(void) { return PA_VERSION; }
+
+extern "C" const char* pa_last_error(const pa_scorer* s) { return s ? s->error.c_str() : g_create_error.c_str(); }
+
+extern "C" void* pa_alloc_pinned(int64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)std::max<int64_t>(bytes, 1)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void pa_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float mod_mass, float mz_error,
+                         const char* fragment_types, int device, pa_scorer** out) {
+    pa_scorer* s = nullptr;
+    if (!out || !mod_group || !fragment_types) return fail(nullptr, PA_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (n_top != PA_N_TOP)
+        return fail(nullptr, PA_ERR_UNSUPPORTED, "n_top must be %d (the reference's score weights have %d entries: "
+                    "smaller n_top reads out of bounds there, larger is ignored)", PA_N_TOP, PA_N_TOP);
+    if (!(bin_size > 0.f)) return fail(nullptr, PA_ERR_ARG, "bin_size must be positive");
+    size_t nt = strlen(fragment_types);
+    if (nt == 0 || nt > 7) return fail(nullptr, PA_ERR_ARG, "fragment_types must hold 1..7 characters");
+    for (size_t i = 0; i < nt; i++)
+        if (!strchr("bcyzZ", fragment_types[i]))
+            return fail(nullptr, PA_ERR_ARG, "fragment type '%c' not in \"bcyzZ\"", fragment_types[i]);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PA_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, PA_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, PA_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    s = new pa_scorer();
+    s->device = device;
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+    s->mod_group = mod_group; s->frag_types = fragment_types;
+    s->bin_size = bin_size; s->mod_mass = mod_mass; s->err = mz_error; s->n_top = n_top;
+    memset(s->nl_mass, 0, sizeof(s->nl_mass));
+    memset(s->nl_has, 0, sizeof(s->nl_has));
+    memset(&s->ctr, 0, sizeof(s->ctr));
+    memset(&s->cfg, 0, sizeof(s->cfg));
+    s->perm_off.assign(64 * 64, -1);
+    // cpp/Ascore.cpp:23-36 + cpp/Util.cpp:52-55 (platform libm, like the reference)
+    for (int d = 1; d <= PA_N_TOP; d++) {
+        float p = (float)((double)((2 * mz_error) * (float)d) / 100.);
+        s->lps[d - 1] = logf(p);
+        s->lpf[d - 1] = (float)log(1. - (double)p);
+    }
+    // saturating binomials
+    std::vector<uint32_t> bin(64 * 64, 0);
+    {
+        std::vector<std::vector<unsigned long long>> C(64, std::vector<unsigned long long>(64, 0));
+        for (int n = 0; n < 64; n++) {
+            C[n][0] = 1;
+            for (int k = 1; k <= n; k++) C[n][k] = std::min<unsigned long long>(C[n - 1][k - 1] + (k <= n - 1 ? C[n - 1][k] : 0), 0xffffffffull);
+            for (int k = 0; k <= n; k++) bin[n * 64 + k] = (uint32_t)C[n][k];
+        }
+    }
+    int rc = PA_OK;
+    auto init = [&]() -> int {
+        CK(s->d_binom.ensure(bin.size() * sizeof(uint32_t)));
+        CK(cudaMemcpy(s->d_binom.p, bin.data(), bin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaStreamCreateWithFlags(&s->slot[i].st, cudaStreamNonBlocking));
+            CK(cudaMallocHost(&s->slot[i].h_totals, sizeof(PlanTotals)));
+            CK(cudaMallocHost(&s->slot[i].h_lookups, sizeof(unsigned long long)));
+            CK(cudaEventCreateWithFlags(&s->slot[i].ev_plan, cudaEventDisableTiming));
+        }
+        CK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_bin_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_tail_table, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_ambiguity, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        int r = refresh_config(s);
+        if (r != PA_OK) return r;
+        return ensure_table(s, PA_TABLE_MIN);
+    };
+    rc = init();
+    if (rc != PA_OK) { g_create_error = s->error; pa_destroy(s); return rc; }
+    *out = s;
+    return PA_OK;
+}
+
+extern "C" int pa_add_neutral_loss(pa_scorer* s, const char* group, float mass) {
+    if (!s || !group) return PA_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    float old_mass[256]; bool old_has[256];
+    memcpy(old_mass, s->nl_mass, sizeof(old_mass)); memcpy(old_has, s->nl_has, sizeof(old_has));
+    for (const char* c = group; *c; c++) { s->nl_mass[(unsigned char)*c] = mass; s->nl_has[(unsigned char)*c] = true; }
+    s->nl_dirty = true;
+    CK(cudaDeviceSynchronize());
+    int rc = refresh_config(s);
+    if (rc != PA_OK) { memcpy(s->nl_mass, old_mass, sizeof(old_mass)); memcpy(s->nl_has, old_has, sizeof(old_has)); s->nl_dirty = true; refresh_config(s); }
+    s->kept.valid = false;
+    return rc;
+}
+
+extern "C" void pa_destroy(pa_scorer* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) s->slot[i].release();
+    s->d_T.release(); s->d_logd.release(); s->d_binom.release(); s->d_nl_sums.release(); s->d_nl_nvar.release();
+    s->d_perm_pool.release(); s->d_perm_off.release();
+    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+    delete s;
+}
+
+// ---- staging helpers ----------------------------------------------------------------------------
+template <class T>
+static cudaError_t stage_in(DevBuf& buf, const T* src, bool on_dev, int64_t lo, int64_t n, cudaStream_t st,
+                            const T** view_abs, int64_t* h2d) {
+    // returns a pointer that can be indexed with ABSOLUTE indices lo..lo+n-1
+    if (src == nullptr) { *view_abs = nullptr; return cudaSuccess; }
+    if (on_dev) { *view_abs = src; return cudaSuccess; }
+    cudaError_t e = buf.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n > 0) {
+        e = cudaMemcpyAsync(buf.p, src + lo, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        *h2d += n * (int64_t)sizeof(T);
+    }
+    *view_abs = buf.as<T>() - lo;
+    return cudaSuccess;
+}
+
+template <class T>
+static cudaError_t stage_out(DevBuf& buf, T* dst, bool on_dev, int64_t lo, int64_t n, T** view_abs) {
+    if (dst == nullptr) { *view_abs = nullptr; return cudaSuccess; }
+    if (on_dev) { *view_abs = dst; return cudaSuccess; }
+    cudaError_t e = buf.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    *view_abs = buf.as<T>() - lo;
+    return cudaSuccess;
+}
+
+template <class T>
+static cudaError_t copy_out(const DevBuf& buf, T* dst, bool on_dev, int64_t lo, int64_t n, cudaStream_t st, int64_t* d2h) {
+    if (dst == nullptr || on_dev || n <= 0) return cudaSuccess;
+    *d2h += n * (int64_t)sizeof(T);
+    return cudaMemcpyAsync(dst + lo, buf.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st);
+}
+
+struct ChunkRange { int64_t p0, p1, s0, s1; };
+
+struct ChunkState {              // what the back half of a chunk needs from the front half
+    ChunkRange r;
+    PaBatchDev b;
+    int64_t mod_lo = 0, mod_hi = 0;
+    const int64_t* mod_off_abs = nullptr;
+    cudaEvent_t e_bin0, e_bin1, e_plan1, e_cnt0, e_cnt1, e_sel1;
+    uint64_t* o_sig; float* o_score; int64_t* o_niso; int32_t* o_nsites; float* o_asc; uint64_t* o_alt; int32_t* o_status;
+};
+
+static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, const ChunkRange& r, int64_t mod_lo,
+                       int64_t mod_hi, int max_peaks, ChunkState& cs) {
+    Slot& sl = s->slot[si];
+    cudaStream_t st = sl.st;
+    const int64_t np = r.p1 - r.p0, ns = r.s1 - r.s0;
+    int64_t peak_lo, peak_hi, pep_lo, pep_hi, aux_lo = 0, aux_hi = 0;
+    if (in_dev) {
+        // offsets live on the device: read the four range ends we need
+        int64_t ends[2]; int32_t pe[2];
+        CK(cudaMemcpy(&ends[0], in->spec_off + r.s0, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&ends[1], in->spec_off + r.s1, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&pe[0], in->pep_off + r.p0, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&pe[1], in->pep_off + r.p1, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        peak_lo = ends[0]; peak_hi = ends[1]; pep_lo = pe[0]; pep_hi = pe[1];
+    } else {
+        peak_lo = in->spec_off[r.s0]; peak_hi = in->spec_off[r.s1];
+        pep_lo = in->pep_off[r.p0]; pep_hi = in->pep_off[r.p1];
+        if (in->aux_off) { aux_lo = in->aux_off[r.p0]; aux_hi = in->aux_off[r.p1]; }
+    }
+    const int64_t npk = peak_hi - peak_lo;
+    cs.r = r; cs.mod_lo = mod_lo; cs.mod_hi = mod_hi;
+    int64_t* h2d = &s->ctr.bytes_h2d;
+    PaBatchDev& b = cs.b;
+    const double *v_mz, *v_int;
+    CK(stage_in(sl.spec_off, in->spec_off, in_dev, r.s0, ns + 1, st, &b.spec_off, h2d));
+    CK(stage_in(sl.mz, in->mz, in_dev, peak_lo, npk, st, &v_mz, h2d));
+    CK(stage_in(sl.inten, in->inten, in_dev, peak_lo, npk, st, &v_int, h2d));
+    CK(stage_in(sl.psm_spec, in->psm_spec, in_dev, r.p0, np, st, &b.psm_spec, h2d));
+    CK(stage_in(sl.pep_off, in->pep_off, in_dev, r.p0, np + 1, st, &b.pep_off, h2d));
+    CK(stage_in(sl.pep, in->pep, in_dev, pep_lo, pep_hi - pep_lo, st, &b.pep, h2d));
+    CK(stage_in(sl.n_mod, in->n_mod, in_dev, r.p0, np, st, &b.n_mod, h2d));
+    CK(stage_in(sl.max_charge, in->max_charge, in_dev, r.p0, np, st, &b.max_charge, h2d));
+    CK(stage_in(sl.aux_off, in->aux_off, in_dev, r.p0, np + 1, st, &b.aux_off, h2d));
+    if (in->aux_off) {
+        CK(stage_in(sl.aux_pos, in->aux_pos, in_dev, aux_lo, aux_hi - aux_lo, st, &b.aux_pos, h2d));
+        CK(stage_in(sl.aux_mass, in->aux_mass, in_dev, aux_lo, aux_hi - aux_lo, st, &b.aux_mass, h2d));
+    } else { b.aux_pos = nullptr; b.aux_mass = nullptr; }
+    CK(stage_in(sl.mod_off, in->mod_off, in_dev, r.p0, np + 1, st, &cs.mod_off_abs, h2d));
+    // PSM-indexed views become chunk-relative
+    b.psm_spec += r.p0; b.pep_off += r.p0; b.n_mod += r.p0; b.max_charge += r.p0;
+    if (b.aux_off) b.aux_off += r.p0;
+    cs.mod_off_abs += r.p0;
+    b.spec_base = 0; b.n_spec = r.s1;   // spectrum indices stay absolute (views are pre-offset)
+
+    // K1 buffers, indexed by absolute peak / spectrum index
+    CK(sl.rmz.ensure((size_t)std::max<int64_t>(npk, 1) * sizeof(float)));
+    CK(sl.rrank.ensure((size_t)std::max<int64_t>(npk, 1)));
+    CK(sl.g_bin.ensure((size_t)std::max<int64_t>(npk, 1) * sizeof(int32_t)));
+    CK(sl.g_tmp.ensure((size_t)std::max<int64_t>(npk, 1)));
+    CK(sl.rcount.ensure((size_t)std::max<int64_t>(ns, 1) * sizeof(int32_t)));
+    PaBinArgs ba;
+    ba.spec_off = b.spec_off + r.s0;          // kernel indexes spectra 0..ns-1
+    ba.mz = v_mz; ba.inten = v_int; ba.peak_base = 0; ba.n_spec = ns;
+    ba.rmz = sl.rmz.as<float>() - peak_lo; ba.rrank = sl.rrank.as<uint8_t>() - peak_lo;
+    ba.g_bin = sl.g_bin.as<int32_t>() - peak_lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - peak_lo;
+    ba.rcount = sl.rcount.as<int32_t>();
+    ba.bin_size = s->bin_size; ba.n_top = s->n_top;
+    int cap = ((std::max(max_peaks, 32) + 31) / 32) * 32;
+    cap = std::min(cap, 4096);
+    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / ((int64_t)cap * 20)));
+    ba.cap = cap;
+    size_t smem = (size_t)wpb * cap * 20;
+    int blocks = (int)std::min<int64_t>((ns + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
+    cs.e_bin0 = next_event(s); cs.e_bin1 = next_event(s); cs.e_plan1 = next_event(s);
+    CK(cudaEventRecord(cs.e_bin0, st));
+    if (ns > 0) {
+        k_bin_topn<<<std::max(blocks, 1), wpb * 32, smem, st>>>(ba);
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches++; s->ctr.launches_bin++;
+    }
+    CK(cudaEventRecord(cs.e_bin1, st));
+    b.rmz = ba.rmz; b.rrank = ba.rrank; b.rcount = sl.rcount.as<int32_t>() - r.s0;
+
+    // plan
+    CK(sl.psm_S.ensure((size_t)(np + 1) * sizeof(int32_t)));
+    CK(sl.psm_status.ensure((size_t)(np + 1) * sizeof(int32_t)));
+    CK(sl.psm_I.ensure((size_t)(np + 1) * sizeof(int64_t)));
+    CK(sl.psm_units.ensure((size_t)(np + 1) * sizeof(int32_t)));
+    CK(sl.iso_off.ensure((size_t)(np + 1) * sizeof(int64_t)));
+    CK(sl.unit_off.ensure((size_t)(np + 1) * sizeof(int32_t)));
+    CK(sl.totals.ensure(sizeof(PlanTotals)));
+    CK(cudaMemsetAsync(sl.totals.p, 0, sizeof(PlanTotals), st));
+    CK(cudaMemsetAsync(sl.psm_I.as<int64_t>() + np, 0, sizeof(int64_t), st));
+    CK(cudaMemsetAsync(sl.psm_units.as<int32_t>() + np, 0, sizeof(int32_t), st));
+    PaPlanOut po;
+    po.psm_S = sl.psm_S.as<int32_t>(); po.psm_status = sl.psm_status.as<int32_t>();
+    po.psm_I = sl.psm_I.as<int64_t>(); po.psm_units = sl.psm_units.as<int32_t>();
+    PlanTotals* dt = sl.totals.as<PlanTotals>();
+    po.combo_bits = dt->combo_bits; po.max_frag = &dt->max_frag; po.max_list = &dt->max_list;
+    if (np > 0) {
+        k_plan<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(s->cfg, b, np, po);
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches++;
+    }
+    size_t t1 = 0, t2 = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t1, po.psm_I, sl.iso_off.as<int64_t>(), (int)(np + 1), st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, po.psm_units, sl.unit_off.as<int32_t>(), (int)(np + 1), st));
+    CK(sl.cub_tmp.ensure(std::max(t1, t2) + 256));
+    size_t tb = sl.cub_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, tb, po.psm_I, sl.iso_off.as<int64_t>(), (int)(np + 1), st));
+    tb = sl.cub_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, tb, po.psm_units, sl.unit_off.as<int32_t>(), (int)(np + 1), st));
+    s->ctr.kernel_launches += 2;
+    CK(cudaMemcpyAsync(&dt->total_iso, sl.iso_off.as<int64_t>() + np, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(&dt->total_units, sl.unit_off.as<int32_t>() + np, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(sl.h_totals, dt, sizeof(PlanTotals), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(cs.e_plan1, st));
+    CK(cudaEventRecord(sl.ev_plan, st));
+    return PA_OK;
+}
+
+static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev, ChunkState& cs, bool keep) {
+    Slot& sl = s->slot[si];
+    cudaStream_t st = sl.st;
+    const ChunkRange& r = cs.r;
+    const int64_t np = r.p1 - r.p0;
+    CK(cudaEventSynchronize(sl.ev_plan));
+    PlanTotals T = *sl.h_totals;
+    const int64_t total_iso = T.total_iso;
+    const int n_units = T.total_units;
+    // tables that depend on what the chunk contains
+    int rc = ensure_table(s, std::max(T.max_frag, 1));
+    if (rc != PA_OK) return rc;
+    for (int S = 0; S < 64; S++)
+        for (int k = 0; k < 64; k++)
+            if ((T.combo_bits[S] >> k) & 1ull) { rc = ensure_perm(s, S, k); if (rc != PA_OK) return rc; }
+    rc = upload_perms(s);
+    if (rc != PA_OK) return rc;
+    // scratch
+    CK(sl.iso_lo.ensure((size_t)std::max<int64_t>(total_iso, 1) * 8));
+    CK(sl.iso_hi.ensure((size_t)std::max<int64_t>(total_iso, 1) * 8));
+    CK(sl.iso_n.ensure((size_t)std::max<int64_t>(total_iso, 1) * 4));
+    CK(sl.iso_w.ensure((size_t)std::max<int64_t>(total_iso, 1) * 4));
+    CK(sl.g_sort.ensure((size_t)std::max<int64_t>(total_iso, 1) * 8));
+    CK(sl.unit_psm.ensure((size_t)std::max(n_units, 1) * 4));
+    PaIso iso;
+    iso.lo = sl.iso_lo.as<unsigned long long>(); iso.hi = sl.iso_hi.as<unsigned long long>();
+    iso.nfrag = sl.iso_n.as<uint32_t>(); iso.w = sl.iso_w.as<float>();
+    cs.e_cnt0 = next_event(s); cs.e_cnt1 = next_event(s); cs.e_sel1 = next_event(s);
+    if (np > 0) {
+        k_expand_units<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(np, sl.unit_off.as<int32_t>(), sl.unit_psm.as<int32_t>());
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches++;
+    }
+    CK(cudaEventRecord(cs.e_cnt0, st));
+    if (n_units > 0) {
+        PaCountArgs ca;
+        ca.n_units = n_units; ca.unit_psm = sl.unit_psm.as<int32_t>(); ca.unit_off = sl.unit_off.as<int32_t>();
+        ca.iso_off = sl.iso_off.as<int64_t>(); ca.psm_S = sl.psm_S.as<int32_t>(); ca.psm_status = sl.psm_status.as<int32_t>();
+        ca.iso = iso; ca.n_lookups = sl.lookups.as<unsigned long long>();
+        const int wpb = 8;
+        int blocks = (int)std::min<int64_t>(((int64_t)n_units + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
+        size_t smem = wpb * sizeof(PsmSmem);
+        if (s->cfg.has_nl) k_count_score<true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+        else k_count_score<false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches++; s->ctr.launches_count++;
+    }
+    CK(cudaEventRecord(cs.e_cnt1, st));
+    // outputs
+    CK(stage_out(sl.o_sig, out->best_sig, out_dev, r.p0, np, &cs.o_sig));
+    CK(stage_out(sl.o_score, out->best_score, out_dev, r.p0, np, &cs.o_score));
+    CK(stage_out(sl.o_niso, out->n_iso, out_dev, r.p0, np, &cs.o_niso));
+    CK(stage_out(sl.o_nsites, out->n_sites, out_dev, r.p0, np, &cs.o_nsites));
+    CK(stage_out(sl.o_asc, out->ascores, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, &cs.o_asc));
+    CK(stage_out(sl.o_alt, out->alt_sites, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, &cs.o_alt));
+    CK(stage_out(sl.o_status, out->psm_status, out_dev, r.p0, np, &cs.o_status));
+    if (np > 0) {
+        PaSelArgs sa;
+        sa.n_psm = np; sa.iso_off = sl.iso_off.as<int64_t>(); sa.psm_S = sl.psm_S.as<int32_t>();
+        sa.psm_status = sl.psm_status.as<int32_t>(); sa.iso = iso;
+        sa.perm_off = s->d_perm_off.as<int64_t>(); sa.perm_pool = s->d_perm_pool.as<uint32_t>();
+        sa.mod_off = cs.mod_off_abs;
+        sa.best_sig = cs.o_sig ? cs.o_sig + r.p0 : nullptr;
+        sa.best_score = cs.o_score ? cs.o_score + r.p0 : nullptr;
+        sa.n_iso = cs.o_niso ? cs.o_niso + r.p0 : nullptr;
+        sa.n_sites = cs.o_nsites ? cs.o_nsites + r.p0 : nullptr;
+        sa.ascores = cs.o_asc; sa.alt_sites = cs.o_alt;            // indexed with absolute mod_off
+        sa.psm_status_out = cs.o_status ? cs.o_status + r.p0 : nullptr;
+        const int wpb = 8;
+        int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * 2);
+        sa.list_stride = ((int64_t)std::max(T.max_list, 1) + 31) / 32 * 32;
+        if (T.max_list > PA_LCAP) CK(sl.g_lists.ensure((size_t)blocks * wpb * 4 * sa.list_stride * sizeof(float)));
+        sa.g_lists = sl.g_lists.as<float>();
+        sa.g_sort = sl.g_sort.as<unsigned long long>();
+        k_select<<<blocks, wpb * 32, wpb * sizeof(SelSmem), st>>>(s->cfg, cs.b, sa);
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches++; s->ctr.launches_select++;
+    }
+    CK(cudaEventRecord(cs.e_sel1, st));
+    int64_t* d2h = &s->ctr.bytes_d2h;
+    CK(copy_out(sl.o_sig, out->best_sig, out_dev, r.p0, np, st, d2h));
+    CK(copy_out(sl.o_score, out->best_score, out_dev, r.p0, np, st, d2h));
+    CK(copy_out(sl.o_niso, out->n_iso, out_dev, r.p0, np, st, d2h));
+    CK(copy_out(sl.o_nsites, out->n_sites, out_dev, r.p0, np, st, d2h));
+    CK(copy_out(sl.o_asc, out->ascores, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, st, d2h));
+    CK(copy_out(sl.o_alt, out->alt_sites, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, st, d2h));
+    CK(copy_out(sl.o_status, out->psm_status, out_dev, r.p0, np, st, d2h));
+    s->ctr.n_isoforms += total_iso;
+    if (keep) {
+        s->kept.b = cs.b; s->kept.n_psm = np; s->kept.psm_lo = r.p0;
+        s->kept.iso_off = sl.iso_off.as<int64_t>(); s->kept.psm_S = sl.psm_S.as<int32_t>();
+        s->kept.psm_status = sl.psm_status.as<int32_t>(); s->kept.iso = iso; s->kept.max_list = T.max_list;
+        s->kept.valid = true; s->kept.slot = si;
+    }
+    return PA_OK;
+}
+
+extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results* out, uint32_t flags) {
+    if (!s) return PA_ERR_ARG;
+    if (!in || !out) return fail(s, PA_ERR_ARG, "NULL batch or results");
+    if (in->n_psm < 0 || in->n_spec < 0) return fail(s, PA_ERR_ARG, "negative sizes");
+    if (in->n_psm > 0 && (!in->spec_off || !in->mz || !in->inten || !in->psm_spec || !in->pep_off || !in->pep ||
+                          !in->n_mod || !in->max_charge || !in->mod_off))
+        return fail(s, PA_ERR_ARG, "NULL input array");
+    if (in->aux_off && (!in->aux_pos || !in->aux_mass)) {
+        // an all-empty aux CSR may come with NULL payload pointers
+    }
+    CK(cudaSetDevice(s->device));
+    int rc = refresh_config(s);
+    if (rc != PA_OK) return rc;
+    memset(&s->ctr, 0, sizeof(s->ctr));
+    s->ev_used = 0;
+    s->kept.valid = false;
+    s->ctr.n_psm = in->n_psm; s->ctr.n_spec = in->n_spec;
+    if (in->n_psm == 0) return PA_OK;
+    const bool in_dev = is_device_ptr(in->mz);
+    const bool out_dev = is_device_ptr(out->best_score ? (void*)out->best_score
+                                       : out->best_sig ? (void*)out->best_sig
+                                       : out->ascores ? (void*)out->ascores : (void*)out->psm_status);
+    const bool keep = (flags & PA_KEEP_ISOFORMS) != 0;
+    for (int i = 0; i < 2; i++) {
+        CK(s->slot[i].lookups.ensure(8));
+        CK(cudaMemsetAsync(s->slot[i].lookups.p, 0, 8, s->slot[i].st));
+    }
+
+    // ---- chunking ----
+    std::vector<ChunkRange> chunks;
+    std::vector<int> chunk_maxp;
+    int64_t mod_total_lo = 0;
+    std::vector<int64_t> mod_lo, mod_hi;
+    if (in_dev || keep) {
+        chunks.push_back({0, in->n_psm, 0, in->n_spec});
+    } else {
+        bool mono = true;
+        for (int64_t p = 1; p < in->n_psm && mono; p++) mono = in->psm_spec[p] >= in->psm_spec[p - 1];
+        for (int64_t p = 0; p < in->n_psm && mono; p++) mono = in->psm_spec[p] >= 0 && in->psm_spec[p] < in->n_spec;
+        if (!mono) chunks.push_back({0, in->n_psm, 0, in->n_spec});
+        else {
+            int64_t p0 = 0;
+            while (p0 < in->n_psm) {
+                int64_t s0 = in->psm_spec[p0];
+                // PSMs sharing the spectrum of p0 that were cut off by the previous chunk stay reachable:
+                // chunk spectra start at the first spectrum referenced
+                int64_t p1 = std::min<int64_t>(p0 + PA_CHUNK_PSM, in->n_psm);
+                while (p1 > p0 + 1 && in->spec_off[in->psm_spec[p1 - 1] + 1] - in->spec_off[s0] > PA_CHUNK_PEAKS) p1 = p0 + (p1 - p0) / 2;
+                int64_t s1 = (int64_t)in->psm_spec[p1 - 1] + 1;
+                chunks.push_back({p0, p1, s0, s1});
+                p0 = p1;
+            }
+        }
+    }
+    (void)mod_total_lo;
+    for (auto& c : chunks) {
+        int mp = 512;
+        if (!in_dev) {
+            int64_t m = 0;
+            for (int64_t q = c.s0; q < c.s1; q++) m = std::max<int64_t>(m, in->spec_off[q + 1] - in->spec_off[q]);
+            mp = (int)std::min<int64_t>(m, 1 << 20);
+            mod_lo.push_back(in->mod_off[c.p0]); mod_hi.push_back(in->mod_off[c.p1]);
+        } else {
+            int64_t e[2];
+            CK(cudaMemcpy(&e[0], in->mod_off + c.p0, 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&e[1], in->mod_off + c.p1, 8, cudaMemcpyDeviceToHost));
+            mod_lo.push_back(e[0]); mod_hi.push_back(e[1]);
+            // spectrum sizes live on the device: reduce the largest one there
+            CK(s->slot[0].totals.ensure(sizeof(PlanTotals)));
+            int* d_max = (int*)s->slot[0].totals.p;
+            CK(cudaMemset(d_max, 0, sizeof(int)));
+            k_max_peaks<<<(unsigned)((c.s1 - c.s0 + 255) / 256), 256>>>(in->spec_off + c.s0, c.s1 - c.s0, d_max);
+            CK(cudaGetLastError());
+            CK(cudaMemcpy(&mp, d_max, sizeof(int), cudaMemcpyDeviceToHost));
+            s->ctr.kernel_launches++;
+        }
+        chunk_maxp.push_back(mp);
+    }
+
+    // ---- two-slot software pipeline ----
+    std::vector<ChunkState> cs(chunks.size());
+    cudaEvent_t e_all0 = next_event(s), e_all1 = next_event(s);
+    CK(cudaEventRecord(e_all0, s->slot[0].st));
+    rc = chunk_front(s, 0, in, in_dev, chunks[0], mod_lo[0], mod_hi[0], chunk_maxp[0], cs[0]);
+    if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
+    for (size_t c = 0; c < chunks.size(); c++) {
+        if (c + 1 < chunks.size()) {
+            // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
+            rc = chunk_front(s, (int)((c + 1) & 1), in, in_dev, chunks[c + 1], mod_lo[c + 1], mod_hi[c + 1],
+                             chunk_maxp[c + 1], cs[c + 1]);
+            if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
+        }
+        rc = chunk_back(s, (int)(c & 1), out, out_dev, cs[c], keep);
+        if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
+    }
+    for (int i = 0; i < 2; i++)
+        CK(cudaMemcpyAsync(s->slot[i].h_lookups, s->slot[i].lookups.p, 8, cudaMemcpyDeviceToHost, s->slot[i].st));
+    CK(cudaStreamSynchronize(s->slot[0].st));
+    CK(cudaStreamSynchronize(s->slot[1].st));
+    CK(cudaEventRecord(e_all1, s->slot[0].st));
+    CK(cudaEventSynchronize(e_all1));
+    // counters
+    for (size_t c = 0; c < chunks.size(); c++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, cs[c].e_bin0, cs[c].e_bin1); s->ctr.ms_bin += ms;
+        cudaEventElapsedTime(&ms, cs[c].e_bin1, cs[c].e_plan1); s->ctr.ms_plan += ms;
+        cudaEventElapsedTime(&ms, cs[c].e_cnt0, cs[c].e_cnt1); s->ctr.ms_count += ms;
+        cudaEventElapsedTime(&ms, cs[c].e_cnt1, cs[c].e_sel1); s->ctr.ms_select += ms;
+    }
+    cudaEventElapsedTime(&s->ctr.ms_total, e_all0, e_all1);
+    s->ctr.n_fragment_lookups = (int64_t)(*s->slot[0].h_lookups) + (int64_t)(*s->slot[1].h_lookups);
+    if (!in_dev) s->ctr.n_peaks = in->spec_off[in->n_spec] - in->spec_off[0];
+    return PA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t pa_fetch_pep_scores(pa_scorer* s, int64_t psm, int64_t cap, uint64_t* sig, int32_t* counts,
+                                       float* scores, float* weighted, int32_t* total_fragments) {
+    if (!s) return PA_ERR_ARG;
+    if (!s->kept.valid) return fail(s, PA_ERR_STATE, "no kept batch: score with PA_KEEP_ISOFORMS first");
+    if (psm < s->kept.psm_lo || psm >= s->kept.psm_lo + s->kept.n_psm) return fail(s, PA_ERR_ARG, "psm index out of range");
+    CK(cudaSetDevice(s->device));
+    const int64_t q = psm - s->kept.psm_lo;
+    int64_t off[2]; int32_t S, k, status;
+    CK(cudaMemcpy(off, s->kept.iso_off + q, 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&S, s->kept.psm_S + q, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&status, s->kept.psm_status + q, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&k, s->kept.b.n_mod + q, 4, cudaMemcpyDeviceToHost));
+    const int64_t I = off[1] - off[0];
+    if (I <= 0 || status != PA_PSM_OK) return 0;
+    DevBuf d_sig, d_cnt, d_sc, d_w, d_tot;
+    CK(d_sig.ensure(I * 8)); CK(d_cnt.ensure(I * PA_N_TOP * 4)); CK(d_sc.ensure(I * PA_N_TOP * 4));
+    CK(d_w.ensure(I * 4)); CK(d_tot.ensure(I * 4));
+    k_export_psm<<<(unsigned)((I + 127) / 128), 128>>>(s->cfg, off[0], I, S, k, s->kept.iso, d_sig.as<uint64_t>(),
+                                                        d_cnt.as<int32_t>(), d_sc.as<float>(), d_w.as<float>(), d_tot.as<int32_t>());
+    CK(cudaGetLastError());
+    std::vector<uint64_t> h_sig(I); std::vector<int32_t> h_cnt(I * PA_N_TOP), h_tot(I);
+    std::vector<float> h_sc(I * PA_N_TOP), h_w(I);
+    CK(cudaMemcpy(h_sig.data(), d_sig.p, I * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_cnt.data(), d_cnt.p, I * PA_N_TOP * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_sc.data(), d_sc.p, I * PA_N_TOP * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_w.data(), d_w.p, I * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_tot.data(), d_tot.p, I * 4, cudaMemcpyDeviceToHost));
+    d_sig.release(); d_cnt.release(); d_sc.release(); d_w.release(); d_tot.release();
+    // listing order: hash-iteration order, then std::sort by descending weighted score unless
+    // the PSM is unambiguous (cpp/Ascore.cpp:263-269)
+    std::vector<uint32_t> order(I);
+    if (I > 1) {
+        int rc = ensure_perm(s, S, k);
+        if (rc != PA_OK) return rc;
+        const uint32_t* perm = s->perm_pool.data() + s->perm_off[S * 64 + k];
+        for (int64_t i = 0; i < I; i++) order[i] = perm[i];
+        if (k < S) {
+            const float* w = h_w.data();
+            std::sort(order.begin(), order.end(), [w](uint32_t a, uint32_t b) { return w[a] > w[b]; });
+        }
+    } else order[0] = 0;
+    for (int64_t i = 0; i < I && i < cap; i++) {
+        uint32_t id = order[i];
+        if (sig) sig[i] = h_sig[id];
+        if (counts) memcpy(counts + i * PA_N_TOP, &h_cnt[id * PA_N_TOP], PA_N_TOP * 4);
+        if (scores) memcpy(scores + i * PA_N_TOP, &h_sc[id * PA_N_TOP], PA_N_TOP * 4);
+        if (weighted) weighted[i] = h_w[id];
+        if (total_fragments) total_fragments[i] = h_tot[id];
+    }
+    return I;
+}
+
+extern "C" int pa_calculate_ambiguity(pa_scorer* s, int64_t psm, uint64_t sig_a, const float* scores_a, float weighted_a,
+                                      uint64_t sig_b, const float* scores_b, float weighted_b, float* out) {
+    if (!s || !scores_a || !scores_b || !out) return PA_ERR_ARG;
+    if (!s->kept.valid) return fail(s, PA_ERR_STATE, "no kept batch: score with PA_KEEP_ISOFORMS first");
+    if (psm < s->kept.psm_lo || psm >= s->kept.psm_lo + s->kept.n_psm) return fail(s, PA_ERR_ARG, "psm index out of range");
+    CK(cudaSetDevice(s->device));
+    PaAmbArgs a;
+    a.psm = psm - s->kept.psm_lo; a.sigA = sig_a; a.sigB = sig_b; a.wA = weighted_a; a.wB = weighted_b;
+    memcpy(a.scA, scores_a, sizeof(a.scA)); memcpy(a.scB, scores_b, sizeof(a.scB));
+    DevBuf d_out, d_lists;
+    CK(d_out.ensure(4));
+    a.list_stride = ((int64_t)std::max(s->kept.max_list, 1) + 31) / 32 * 32;
+    if (s->kept.max_list > PA_LCAP) CK(d_lists.ensure((size_t)4 * a.list_stride * sizeof(float)));
+    a.g_lists = d_lists.as<float>(); a.out = d_out.as<float>();
+    k_ambiguity<<<1, 32, sizeof(SelSmem)>>>(s->cfg, s->kept.b, a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, d_out.p, 4, cudaMemcpyDeviceToHost));
+    d_out.release(); d_lists.release();
+    return PA_OK;
+}
+
+// cpp/ModifiedPeptide.cpp:184-193
+extern "C" int pa_site_positions(const pa_scorer* s, const uint8_t* pep, int32_t len, int32_t* pos, int32_t cap) {
+    if (!s || !pep) return PA_ERR_ARG;
+    bool has_n = s->mod_group.find('n') != std::string::npos, has_c = s->mod_group.find('c') != std::string::npos;
+    int n = 0;
+    for (int i = 0; i < len; i++) {
+        bool site = s->mod_group.find((char)pep[i]) != std::string::npos || (has_n && i == 0) || (has_c && i == len - 1);
+        if (site) { if (pos && n < cap) pos[n] = i + 1; n++; }
+    }
+    return n;
+}
+
+// cpp/ModifiedPeptide.cpp:199-253
+extern "C" int pa_format_sequence(const pa_scorer* s, const uint8_t* pep, int32_t len, int32_t n_mod,
+                                  const uint32_t* aux_pos, const float* aux_mass, int32_t n_aux, uint64_t sig,
+                                  char* buf, int32_t cap) {
+    if (!s || !pep || !buf || len < 0) return PA_ERR_ARG;
+    std::vector<float> mm(len + 2, 0.f);
+    std::vector<int> sites;
+    bool has_n = s->mod_group.find('n') != std::string::npos, has_c = s->mod_group.find('c') != std::string::npos;
+    for (int i = 0; i < len; i++)
+        if (s->mod_group.find((char)pep[i]) != std::string::npos || (has_n && i == 0) || (has_c && i == len - 1)) sites.push_back(i);
+    if (n_mod > (int)sites.size()) { if (has_n) mm.front() += s->mod_mass; else mm.back() += s->mod_mass; }
+    for (size_t j = 0; j < sites.size() && j < 64; j++) {
+        if (!((sig >> j) & 1ull)) continue;
+        int p = sites[j];
+        if (s->mod_group.find((char)pep[p]) != std::string::npos) mm[p + 1] += s->mod_mass;
+        else if (p == 0) mm.front() += s->mod_mass;
+        else if (p + 1 == len) mm.back() += s->mod_mass;
+    }
+    for (int a = 0; a < n_aux; a++) if (aux_pos[a] < mm.size()) mm[aux_pos[a]] += aux_mass[a];
+    std::string o;
+    size_t start = (mm.front() == 0.f) ? 1 : 0, end = (mm.back() == 0.f) ? mm.size() - 1 : mm.size();
+    for (size_t i = start; i < end; i++) {
+        o += (i == 0) ? 'n' : (i == (size_t)len + 1) ? 'c' : (char)pep[i - 1];
+        if (mm[i] > 0.f) { char t[16]; snprintf(t, sizeof(t), "[%d]", (int)std::round(mm[i])); o += t; }
+    }
+    if ((int)o.size() + 1 > cap) return -(int)o.size() - 1;
+    memcpy(buf, o.c_str(), o.size() + 1);
+    return (int)o.size();
+}
+
+extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_off, const double* mz,
+                              const double* inten, float* out_mz, uint8_t* out_rank, int32_t* out_count) {
+    if (!s || !spec_off || !mz || !inten || !out_mz || !out_rank || !out_count) return PA_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    if (n_spec <= 0) return PA_OK;
+    if (is_device_ptr(mz)) return fail(s, PA_ERR_ARG, "pa_bin_spectra takes host arrays");
+    Slot& sl = s->slot[0];
+    cudaStream_t st = sl.st;
+    const int64_t lo = spec_off[0], npk = spec_off[n_spec] - lo;
+    int64_t dummy = 0;
+    const int64_t* v_off; const double *v_mz, *v_int;
+    CK(stage_in(sl.spec_off, spec_off, false, 0, n_spec + 1, st, &v_off, &dummy));
+    CK(stage_in(sl.mz, mz, false, lo, npk, st, &v_mz, &dummy));
+    CK(stage_in(sl.inten, inten, false, lo, npk, st, &v_int, &dummy));
+    CK(sl.rmz.ensure((size_t)std::max<int64_t>(npk, 1) * 4)); CK(sl.rrank.ensure((size_t)std::max<int64_t>(npk, 1)));
+    CK(sl.g_bin.ensure((size_t)std::max<int64_t>(npk, 1) * 4)); CK(sl.g_tmp.ensure((size_t)std::max<int64_t>(npk, 1)));
+    CK(sl.rcount.ensure((size_t)n_spec * 4));
+    int64_t m = 0;
+    for (int64_t q = 0; q < n_spec; q++) m = std::max<int64_t>(m, spec_off[q + 1] - spec_off[q]);
+    PaBinArgs ba;
+    ba.spec_off = v_off; ba.mz = v_mz; ba.inten = v_int; ba.peak_base = 0; ba.n_spec = n_spec;
+    ba.rmz = sl.rmz.as<float>() - lo; ba.rrank = sl.rrank.as<uint8_t>() - lo;
+    ba.g_bin = sl.g_bin.as<int32_t>() - lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - lo;
+    ba.rcount = sl.rcount.as<int32_t>(); ba.bin_size = s->bin_size; ba.n_top = s->n_top;
+    int cap = (int)std::min<int64_t>(((std::max<int64_t>(m, 32) + 31) / 32) * 32, 4096);
+    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / ((int64_t)cap * 20)));
+    ba.cap = cap;
+    int blocks = (int)std::min<int64_t>((n_spec + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
+    k_bin_topn<<<blocks, wpb * 32, (size_t)wpb * cap * 20, st>>>(ba);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_mz + lo, sl.rmz.p, (size_t)npk * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_rank + lo, sl.rrank.p, (size_t)npk, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_count, sl.rcount.p, (size_t)n_spec * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PA_OK;
+}
+
+extern "C" int pa_tail_table(pa_scorer* s, int32_t n_max, float* out) {
+    if (!s || !out || n_max < 0) return PA_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_table(s, n_max);
+    if (rc != PA_OK) return rc;
+    size_t entries = ((size_t)n_max + 1) * ((size_t)n_max + 2) / 2;
+    CK(cudaMemcpy(out, s->d_T.p, entries * PA_N_TOP * sizeof(float), cudaMemcpyDeviceToHost));
+    return PA_OK;
+}
+
+extern "C" int pa_counters(const pa_scorer* s, pa_counters_t* out) {
+    if (!s || !out) return PA_ERR_ARG;
+    *out = s->ctr;
+    return PA_OK;
+}
