@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--psms", type=int, default=0, help="PSMs per GPU per step (default: the BASELINE size)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -286,10 +288,12 @@ def main():
     barrier()
     wall_dev = time.perf_counter() - t_wall
     # ---- e2e: host buffers through the public API ----
-    run_steps(host, out_host, max(1, min(args.warmup, 2)))
+    e2e_steps = 1 if args.no_e2e else args.steps
+    run_steps(host, out_host, 1 if args.no_e2e else max(1, min(args.warmup, 2)))
     barrier()
     t_wall = time.perf_counter()
-    ms_e2e, ctr_e2e = run_steps(host, out_host, args.steps)
+    ms_e2e, ctr_e2e = run_steps(host, out_host, e2e_steps)
+    ms_e2e *= args.steps / e2e_steps
     barrier()
     wall_e2e = time.perf_counter() - t_wall
     clocks = sampler.stop()
@@ -346,7 +350,7 @@ def main():
             "isoforms_per_step": int(ctr_dev["n_isoforms"]), "fragment_lookups_per_step": int(ctr_dev["n_fragment_lookups"]),
             "host_and_device_paths_bit_identical": bool(same), "psms_not_scored": n_bad, "gen_seconds": gen_s,
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu_baseline:
             # CPU reference on this box's host cores, in a fresh process (no fork after CUDA init)
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
                    "--workload", args.workload, "--seed", str(args.seed), "--psms", str(n_psm)]

@@ -1,0 +1,79 @@
+"""CPU, only where oracle/_ref (the compiled, unmodified reference) is present: the C restatement
+against the real thing on fresh seeded inputs, plus unit checks of the two libstdc++ models."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import cscorer
+from pyascore_b200 import synth
+
+pytestmark = pytest.mark.skipif(not cscorer.available("refshim_"), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def _same(a, b):
+    return a.shape == b.shape and a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("workload,n,seed", [("lowres_phospho", 250, 101), ("hires_phospho_nl", 150, 102),
+                                             ("acetyl_k", 210, 103)])
+def test_oracle_equals_reference_on_synthetic(workload, n, seed):
+    w = synth.WORKLOADS[workload]
+    batch = synth.make_batch(workload, n, seed=seed, chunk_index=5)
+    R = cscorer.RefPyAscore(**w["scorer"])
+    O = cscorer.OraclePyAscore(**w["scorer"])
+    for g, m in w["neutral_losses"]:
+        R.add_neutral_loss(g, m)
+        O.add_neutral_loss(g, m)
+    for i in range(batch["n_mod"].size):
+        a = synth.psm_view(batch, i)
+        R.score(*a)
+        O.score(*a)
+        assert all(_same(x, y) for x, y in zip(R.pep_score_tables(), O.pep_score_tables())), i
+        assert R.best_sequence == O.best_sequence and R.sequences() == O.sequences()
+        assert _same(R.ascores, O.ascores)
+        assert all(_same(x, y) for x, y in zip(R.alt_sites, O.alt_sites))
+
+
+def test_math_helpers_equal_reference():
+    Lr, Lo = cscorer.lib("refshim_"), cscorer.lib("orc_")
+    rng = np.random.default_rng(0)
+    for a, b in rng.uniform(-60, 0, (200, 2)):
+        assert Lr.refshim_log_sum(a, b) == Lo.refshim_log_sum(a, b)
+    for n in (1, 2, 7, 34, 68, 312):
+        for k in range(0, n + 1, max(1, n // 17)):
+            assert Lr.refshim_log_bin_coef(k, n) == Lo.refshim_log_bin_coef(k, n)
+    for p in (0.01, 0.0004, 0.1):
+        br, bo = Lr.refshim_binom_new(p), Lo.refshim_binom_new(p)
+        for n in (5, 34, 150):
+            for k in range(1, n + 1, 3):
+                assert Lr.refshim_binom_log10_pvalue(br, k, n) == Lo.refshim_binom_log10_pvalue(bo, k, n)
+                assert Lr.refshim_binom_log_pmf(br, k, n) == Lo.refshim_binom_log_pmf(bo, k, n)
+        Lr.refshim_binom_free(br)
+        Lo.refshim_binom_free(bo)
+
+
+def test_power_set_sum_equals_reference():
+    Lr, Lo = cscorer.lib("refshim_"), cscorer.lib("orc_")
+    cases = [[], [18.01528], [18.01528, 18.01528], [97.9769, 18.01528, 97.9769], [1., 2., 3., 4.], [0.1, 0.2, 0.3]]
+    for v in cases:
+        arr = np.array(v, np.float32)
+        a, b = np.zeros(64, np.float32), np.zeros(64, np.float32)
+        na = Lr.refshim_power_set_sum(arr.ctypes.data if arr.size else None, arr.size, 2, a.ctypes.data, 64)
+        nb = Lo.refshim_power_set_sum(arr.ctypes.data if arr.size else None, arr.size, 2, b.ctypes.data, 64)
+        assert na == nb and _same(a[:na], b[:nb]), v
+
+
+def test_all_tie_order_equals_reference():
+    """no peak matches -> every isoform scores 0 -> pep_scores lists the raw libstdc++ order
+    (hash iteration + introsort on all-equal keys); n = 15, 56, 210, 792"""
+    mz, it = np.array([5000., 5001.]), np.array([1., 2.])
+    for ft in ("by", "yb"):
+        R = cscorer.RefPyAscore(100., 10, "STY", 79.966331, 0.5, ft)
+        O = cscorer.OraclePyAscore(100., 10, "STY", 79.966331, 0.5, ft)
+        for s, k in ((6, 2), (8, 3), (10, 4), (12, 5)):
+            pep = "A" + "S" * s + "K"
+            R.score(mz, it, pep, k, 1)
+            O.score(mz, it, pep, k, 1)
+            assert R.sequences() == O.sequences(), (ft, s, k)
+            assert R.best_sequence == O.best_sequence
