@@ -10,7 +10,8 @@
 #include "../../include/pyascore_b200.h"
 
 #define PA_LMAX 128          // smem rows per peptide (PA_MAX_PEPTIDE + 2)
-#define PA_RCAP 256          // retained peaks staged in shared memory per PSM (else read from global)
+#define PA_RCAP 255          // retained peaks staged in shared memory per PSM (else read from global)
+#define PA_NCELL 256         // m/z cells of the per-PSM peak index (first peak at or after each cell)
 #define PA_UNIT 1024         // isoforms per K2 work unit
 #define PA_FULL 0xffffffffu
 
@@ -160,8 +161,9 @@ struct PsmSmem {
     float res[PA_LMAX][2];        // residue mass: [i][0] plain, [i][1] with the variable mod
     uint8_t nlidx[PA_LMAX][2];    // neutral-loss index per state (0 = none)
     uint8_t site_pos[64];         // residue index of site j
-    float pm[PA_RCAP];            // retained peaks, (float)mz ascending
-    uint8_t pr[PA_RCAP];          // their ranks
+    float pm[PA_RCAP + 1];        // retained peaks, (float)mz ascending
+    uint8_t pr[PA_RCAP + 1];      // their ranks
+    uint8_t cell[PA_NCELL];       // cell[c] = index of the first peak whose cell is >= c
 };
 
 struct PsmInfo {
@@ -169,7 +171,15 @@ struct PsmInfo {
     int status;
     const float* pm;              // -> smem or global
     const uint8_t* pr;
+    const uint8_t* cell;          // -> smem cell index, or nullptr (binary search over global peaks)
+    float cell_base, cell_inv;    // cell(x) = clamp(floor((x - base) * inv), 0, PA_NCELL-1)
 };
+
+__device__ __forceinline__ int pa_cell(float x, float base, float inv) {
+    float c = floorf(__fmul_rn(__fsub_rn(x, base), inv));
+    c = fminf(fmaxf(c, 0.f), (float)(PA_NCELL - 1));
+    return (int)c;
+}
 
 struct PaBatchDev {               // device views of one chunk
     const int64_t* spec_off;
@@ -257,9 +267,31 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
             for (int i = lane; i < R; i += 32) { sm->pm[i] = b.rmz[off + i]; sm->pr[i] = b.rrank[off + i]; }
             info.pm = sm->pm;
             info.pr = sm->pr;
+            info.cell = sm->cell;
+            __syncwarp();
+            // peak index: cell width = power of two so that the peak range spans < PA_NCELL cells.
+            // pa_cell is monotone in x, so every peak before cell[pa_cell(lo)] is <= lo.
+            const float base = R > 0 ? sm->pm[0] : 0.f;
+            const float range = R > 0 ? __fsub_rn(sm->pm[R - 1], base) : 0.f;
+            int e = 0;
+            if (range > 0.f) e = ilogbf(__fmul_rn(range, 1.0f / PA_NCELL)) + 1;
+            e = e < -20 ? -20 : (e > 60 ? 60 : e);
+            const float inv = ldexpf(1.0f, -e);
+            info.cell_base = base;
+            info.cell_inv = inv;
+            for (int j = lane; j < R; j += 32) {
+                const int cj = pa_cell(sm->pm[j], base, inv);
+                const int cp = j > 0 ? pa_cell(sm->pm[j - 1], base, inv) : -1;
+                for (int c = cp + 1; c <= cj; c++) sm->cell[c] = (uint8_t)j;
+                if (j == R - 1) for (int c = cj + 1; c < PA_NCELL; c++) sm->cell[c] = (uint8_t)R;
+            }
+            if (R == 0) for (int c = lane; c < PA_NCELL; c += 32) sm->cell[c] = 0;
         } else {
             info.pm = b.rmz + off;
             info.pr = b.rrank + off;
+            info.cell = nullptr;
+            info.cell_base = 0.f;
+            info.cell_inv = 0.f;
         }
         __syncwarp();
     }
@@ -267,13 +299,22 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
 
 // rank of the best (most intense) retained peak matching theoretical fragment f, or 255.
 // cpp/ModifiedPeptide.cpp:126-142 seen from the fragment's side (SURVEY.md section 7.3 "Matching").
-__device__ __forceinline__ int pa_match_rank(const float* pm, const uint8_t* pr, int R, float f, float err,
-                                             int err_gt_half) {
+__device__ __forceinline__ int pa_match_rank(const PsmInfo& info, float f, float err, int err_gt_half) {
+    const float* pm = info.pm;
+    const uint8_t* pr = info.pr;
+    const int R = info.R;
     const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
-    int a = 0, n = R;                       // first index with pm > lo
-    while (n > 0) {
-        int h = n >> 1;
-        if (!(pm[a + h] > lo)) { a += h + 1; n -= h + 1; } else n = h;
+    int a;
+    if (info.cell != nullptr) {
+        a = info.cell[pa_cell(lo, info.cell_base, info.cell_inv)];
+        while (a < R && !(pm[a] > lo)) a++;
+    } else {
+        a = 0;
+        int n = R;                          // first index with pm > lo
+        while (n > 0) {
+            int h = n >> 1;
+            if (!(pm[a + h] > lo)) { a += h + 1; n -= h + 1; } else n = h;
+        }
     }
     int best = 255;
     for (; a < R; a++) {
@@ -296,11 +337,27 @@ __device__ __forceinline__ double pa_type_adjust(double d, char type) {
 }
 
 __device__ __forceinline__ float pa_charge_mz(double d, int z) {
+    // (d + z * 1.007825) / z  (cpp/ModifiedPeptide.cpp:585-587).  Dividing by 1, 2 or 4 is exact
+    // scaling, so the IEEE division routine is only needed for the other charges.
     if (z > 0) {
-        double zd = (double)z;
-        d = __ddiv_rn(__dadd_rn(d, __dmul_rn(zd, 1.007825)), zd);
+        const double zd = (double)z;
+        const double t = __dadd_rn(d, __dmul_rn(zd, 1.007825));
+        if (z == 1) d = t;
+        else if (z == 2) d = __dmul_rn(t, 0.5);
+        else if (z == 4) d = __dmul_rn(t, 0.25);
+        else d = __ddiv_rn(t, zd);
     }
     return __double2float_rn(d);
+}
+
+// branch-free form of pa_type_adjust: d + A1 - A2 with A = 0 where the reference does nothing
+// (x + 0.0 and x - 0.0 are exact, so the bits are those of the branched form)
+__device__ __forceinline__ void pa_type_consts(char type, double& a1, double& a2) {
+    a1 = 0.; a2 = 0.;
+    if (type == 'y') a1 = 18.010565;
+    else if (type == 'z') { a1 = 18.010565; a2 = 17.026549; }
+    else if (type == 'Z') { a1 = 18.010565; a2 = 16.018724; }
+    else if (type == 'c') a1 = 17.026549;
 }
 
 __device__ __forceinline__ int pa_nl_bump(int state, int idx) {   // idx 1-based

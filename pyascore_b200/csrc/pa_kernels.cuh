@@ -76,37 +76,69 @@ struct PaBinArgs {
     int cap;                 // peaks per warp slot in shared memory
 };
 
+#define PA_NBIN_SMEM 128     // bins whose [start,end) ranges are tabulated in shared memory
+
+// shared memory per warp slot: mz f64[cap] | key u64[cap] | bin i32[cap] | bstart u16[128] | bend u16[128]
+#define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 20 + PA_NBIN_SMEM * 4)
+
+__device__ __forceinline__ void pa_cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int cap = a.cap;
-    double* s_mz = (double*)smem_raw + (size_t)wib * cap;
-    uint64_t* s_key = (uint64_t*)((double*)smem_raw + (size_t)wpb * cap) + (size_t)wib * cap;
-    int32_t* s_bin = (int32_t*)((uint64_t*)((double*)smem_raw + (size_t)wpb * cap) + (size_t)wpb * cap) + (size_t)wib * cap;
+    unsigned char* slot = smem_raw + (size_t)wib * PA_BIN_SLOT_BYTES(cap);
+    double* s_mz = (double*)slot;
+    uint64_t* s_key = (uint64_t*)(slot + (size_t)cap * 8);
+    int32_t* s_bin = (int32_t*)(slot + (size_t)cap * 16);
+    uint16_t* s_bstart = (uint16_t*)(slot + (size_t)cap * 20);
+    uint16_t* s_bend = s_bstart + PA_NBIN_SMEM;
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const int n_top = a.n_top;
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
 
     for (int64_t s = gw; s < a.n_spec; s += nw) {
         const int64_t off = a.spec_off[s] - a.peak_base;
         const int P = (int)(a.spec_off[s + 1] - a.spec_off[s]);
         if (P <= 0) { if (lane == 0) a.rcount[s] = 0; continue; }
         const bool fits = P <= cap;
-        // pass 1: min / max / sortedness (+ stage)
-        double mn = __longlong_as_double(0x7ff0000000000000ll), mx = -mn, carry = -mn;
+        double mn = INF, mx = -INF;
         bool sorted = true;
-        for (int base = 0; base < P; base += 32) {
-            int i = base + lane;
-            double m = 0., it = 0.;
-            if (i < P) { m = a.mz[off + i]; it = a.inten[off + i]; }
-            double prev = __shfl_up_sync(PA_FULL, m, 1);
-            if (lane == 0) prev = carry;
-            if (i < P) {
+        if (fits) {
+            // stage the whole spectrum with asynchronous 8-byte copies: every load of the warp is
+            // in flight at once (the arrays are only 8-byte aligned at a CSR offset)
+            for (int i = lane; i < P; i += 32) {
+                pa_cp_async8(&s_mz[i], a.mz + off + i);
+                pa_cp_async8(&s_key[i], a.inten + off + i);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncwarp();
+            for (int i = lane; i < P; i += 32) {
+                const double m = s_mz[i];
+                const double prev = i > 0 ? s_mz[i - 1] : -INF;
                 if (m < prev) sorted = false;
                 mn = m < mn ? m : mn;
                 mx = m > mx ? m : mx;
-                if (fits) { s_mz[i] = m; s_key[i] = pa_inten_key(it); }
             }
-            carry = __shfl_sync(PA_FULL, m, 31);
+        } else {
+            double carry = -INF;
+            for (int base = 0; base < P; base += 32) {
+                int i = base + lane;
+                double m = 0.;
+                if (i < P) m = a.mz[off + i];
+                double prev = __shfl_up_sync(PA_FULL, m, 1);
+                if (lane == 0) prev = carry;
+                if (i < P) {
+                    if (m < prev) sorted = false;
+                    mn = m < mn ? m : mn;
+                    mx = m > mx ? m : mx;
+                }
+                carry = __shfl_sync(PA_FULL, m, 31);
+            }
         }
         for (int o = 16; o > 0; o >>= 1) {
             double t = __shfl_xor_sync(PA_FULL, mn, o); mn = t < mn ? t : mn;
@@ -121,24 +153,56 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
         const double dmin = (double)min_mz, dbs = (double)a.bin_size;
 
         if (fits && sorted) {
-            __syncwarp();
-            for (int i = lane; i < P; i += 32) {
-                double q = floor(__ddiv_rn(__dsub_rn(s_mz[i], dmin), dbs));
-                long long bq = (long long)q;
-                if (bq > n_bins - 1) bq = n_bins - 1;
-                s_bin[i] = (int32_t)bq;
+            const bool tab = n_bins <= PA_NBIN_SMEM;
+            // bins; a sorted spectrum makes every bin one contiguous run [bstart, bend)
+            int carry_bin = -1;
+            for (int base = 0; base < P; base += 32) {
+                const int i = base + lane;
+                int bq = -1;
+                if (i < P) {
+                    double q = floor(__ddiv_rn(__dsub_rn(s_mz[i], dmin), dbs));
+                    long long b64 = (long long)q;
+                    if (b64 > n_bins - 1) b64 = n_bins - 1;
+                    bq = (int)b64;
+                    s_bin[i] = bq;
+                    s_key[i] = pa_inten_key(__longlong_as_double((long long)s_key[i]));
+                }
+                int bprev = __shfl_up_sync(PA_FULL, bq, 1);
+                if (lane == 0) bprev = carry_bin;
+                if (tab && i < P) {
+                    if (bq != bprev) { s_bstart[bq] = (uint16_t)i; if (i > 0) s_bend[bprev] = (uint16_t)i; }
+                    if (i == P - 1) s_bend[bq] = (uint16_t)P;
+                }
+                carry_bin = __shfl_sync(PA_FULL, bq, 31);
             }
             __syncwarp();
             int out = 0;
             for (int base = 0; base < P; base += 32) {
-                int i = base + lane;
+                const int i = base + lane;
                 int cnt = n_top;
                 if (i < P) {
                     const int bq = s_bin[i];
                     const uint64_t ki = s_key[i];
                     cnt = 0;
-                    for (int j = i - 1; j >= 0 && cnt < n_top && s_bin[j] == bq; j--) cnt += (s_key[j] >= ki);
-                    for (int j = i + 1; j < P && cnt < n_top && s_bin[j] == bq; j++) cnt += (s_key[j] > ki);
+                    if (tab) {
+                        const int b0 = s_bstart[bq], b1 = s_bend[bq];
+                        // rank = peaks of the same bin that beat this one (earlier index wins ties)
+                        int j = b0;
+                        for (; j + 4 <= i && cnt < n_top; j += 4) {
+                            const uint64_t k0 = s_key[j], k1 = s_key[j + 1], k2 = s_key[j + 2], k3 = s_key[j + 3];
+                            cnt += (k0 >= ki) + (k1 >= ki) + (k2 >= ki) + (k3 >= ki);
+                        }
+                        for (; j < i; j++) cnt += (s_key[j] >= ki);
+                        j = i + 1;
+                        for (; j + 4 <= b1 && cnt < n_top; j += 4) {
+                            const uint64_t k0 = s_key[j], k1 = s_key[j + 1], k2 = s_key[j + 2], k3 = s_key[j + 3];
+                            cnt += (k0 > ki) + (k1 > ki) + (k2 > ki) + (k3 > ki);
+                        }
+                        for (; j < b1; j++) cnt += (s_key[j] > ki);
+                    } else {
+                        for (int j = i - 1; j >= 0 && cnt < n_top && s_bin[j] == bq; j--) cnt += (s_key[j] >= ki);
+                        for (int j = i + 1; j < P && cnt < n_top && s_bin[j] == bq; j++) cnt += (s_key[j] > ki);
+                    }
                 }
                 const bool keep = cnt < n_top;
                 unsigned bal = __ballot_sync(PA_FULL, keep);
@@ -291,21 +355,25 @@ struct PaCountArgs {
     unsigned long long* n_lookups;   // counter
 };
 
-// Walk all fragments of the isoform with residue mask (mlo,mhi); returns packed non-cumulative counts.
+// Walk the fragments of ion types [t0, t1) of the isoform with residue mask (mlo,mhi); returns
+// packed non-cumulative per-rank counts.
 template <bool HAS_NL>
 __device__ __forceinline__ void pa_walk_isoform(const PaCfg& cfg, const PsmSmem* sm, const PsmInfo& info,
-                                                uint64_t mlo, uint64_t mhi, unsigned long long& clo,
-                                                unsigned long long& chi, uint32_t& nfrag) {
-    const int L = info.L, Z = info.Z, R = info.R;
+                                                uint64_t mlo, uint64_t mhi, int t0, int t1,
+                                                unsigned long long& clo, unsigned long long& chi,
+                                                uint32_t& nfrag) {
+    const int L = info.L, Z = info.Z;
     clo = 0; chi = 0; nfrag = 0;
-    for (int t = 0; t < cfg.n_types; t++) {
+    // L == 1: the walk starts on the last residue and the reference's end test lets all but
+    // the last neutral-loss variant through (cpp/ModifiedPeptide.cpp:516-524)
+    const int steps = (L == 1) ? 1 : L - 1;
+    for (int t = t0; t < t1; t++) {
         const char type = cfg.types[t];
         const bool fwd = (type == 'b' || type == 'c');
+        double a1, a2;
+        pa_type_consts(type, a1, a2);
         float run = 0.f;
         int nls = 0;
-        // L == 1: the walk starts on the last residue and the reference's end test lets all but
-        // the last neutral-loss variant through (cpp/ModifiedPeptide.cpp:516-524)
-        const int steps = (L == 1) ? 1 : L - 1;
         for (int step = 0; step < steps; step++) {
             const int i = fwd ? step : L - 1 - step;
             const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
@@ -321,10 +389,10 @@ __device__ __forceinline__ void pa_walk_isoform(const PaCfg& cfg, const PsmSmem*
             for (int v = 0; v < nv; v++) {
                 float base = run;
                 if (HAS_NL) base = __fsub_rn(run, __ldg(cfg.nl_sums + nls * 16 + v));
-                const double d = pa_type_adjust((double)base, type);
+                const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
                 for (int z = 1; z <= Z; z++) {
                     const float f = pa_charge_mz(d, z);
-                    const int rk = pa_match_rank(info.pm, info.pr, R, f, cfg.err, cfg.err_gt_half);
+                    const int rk = pa_match_rank(info, f, cfg.err, cfg.err_gt_half);
                     if (rk < 5) clo += 1ull << (12 * rk);
                     else if (rk < 10) chi += 1ull << (12 * (rk - 5));
                 }
@@ -369,7 +437,9 @@ __device__ __forceinline__ void pa_sites_to_mask(const PsmSmem* sm, uint64_t bit
     }
 }
 
-template <bool HAS_NL>
+// PAIR: exactly two ion types (the default "by"): adjacent lanes take the two types of one isoform
+// and add their counts with one shuffle, so small PSMs keep twice as many lanes busy.
+template <bool HAS_NL, bool PAIR>
 __global__ void __launch_bounds__(256) k_count_score(PaCfg cfg, PaBatchDev b, PaCountArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -385,18 +455,31 @@ __global__ void __launch_bounds__(256) k_count_score(PaCfg cfg, PaBatchDev b, Pa
         const int64_t I = a.iso_off[p + 1] - a.iso_off[p];
         const int64_t first = (int64_t)(u - a.unit_off[p]) * PA_UNIT;
         const int64_t cnt = (I - first < PA_UNIT) ? I - first : PA_UNIT;
-        for (int64_t q = lane; q < cnt; q += 32) {
-            const uint32_t idx = (uint32_t)(first + q);
-            const uint64_t bits = pa_unrank(cfg.binom, S, k, idx);
-            uint64_t mlo, mhi;
-            pa_sites_to_mask(sm, bits, mlo, mhi);
-            unsigned long long clo, chi; uint32_t nf;
-            pa_walk_isoform<HAS_NL>(cfg, sm, info, mlo, mhi, clo, chi, nf);
-            pa_cumulate(clo, chi);
-            const int64_t g = a.iso_off[p] + idx;
-            a.iso.lo[g] = clo; a.iso.hi[g] = chi; a.iso.nfrag[g] = nf;
-            a.iso.w[g] = pa_weighted(cfg, clo, chi, (int)nf);
-            lookups += nf;
+        const int64_t items = PAIR ? 2 * cnt : cnt;
+        for (int64_t q0 = 0; q0 < items; q0 += 32) {
+            const int64_t q = q0 + lane;
+            const bool active = q < items;
+            const uint32_t idx = (uint32_t)(first + (PAIR ? (q >> 1) : q));
+            unsigned long long clo = 0, chi = 0; uint32_t nf = 0;
+            if (active) {
+                const uint64_t bits = pa_unrank(cfg.binom, S, k, idx);
+                uint64_t mlo, mhi;
+                pa_sites_to_mask(sm, bits, mlo, mhi);
+                const int t0 = PAIR ? (int)(q & 1) : 0, t1 = PAIR ? t0 + 1 : cfg.n_types;
+                pa_walk_isoform<HAS_NL>(cfg, sm, info, mlo, mhi, t0, t1, clo, chi, nf);
+                lookups += nf;
+            }
+            if (PAIR) {
+                clo += __shfl_xor_sync(PA_FULL, clo, 1);
+                chi += __shfl_xor_sync(PA_FULL, chi, 1);
+                nf += __shfl_xor_sync(PA_FULL, nf, 1);
+            }
+            if (active && (!PAIR || (lane & 1) == 0)) {
+                pa_cumulate(clo, chi);
+                const int64_t g = a.iso_off[p] + idx;
+                a.iso.lo[g] = clo; a.iso.hi[g] = chi; a.iso.nfrag[g] = nf;
+                a.iso.w[g] = pa_weighted(cfg, clo, chi, (int)nf);
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) lookups += __shfl_xor_sync(PA_FULL, lookups, o);
@@ -408,8 +491,8 @@ __global__ void __launch_bounds__(256) k_count_score(PaCfg cfg, PaBatchDev b, Pa
 // cpp/Ascore.cpp:38-51 (unambiguous), :141-146 (std::sort), :212-254 (calculateAscores),
 // :157-210 (calculateAmbiguity), cpp/ModifiedPeptide.cpp:259-320 (site-determining ions).
 // ---------------------------------------------------------------------------------------------
-#define PA_LCAP 320      // fragments per (isoform, ion type) list staged in shared memory
-#define PA_SORTCAP 320   // isoforms sortable in shared memory (aliases the list area)
+#define PA_LCAP 256      // fragments per (isoform, ion type) list staged in shared memory (power of two)
+#define PA_SORTCAP 256   // isoforms sortable in shared memory (aliases the list area)
 
 struct SelSmem {
     PsmSmem psm;
@@ -572,9 +655,17 @@ __device__ __forceinline__ void pa_sdi_type(const PaCfg& cfg, SelSmem* sm, const
     }
     __syncwarp();
     const int nA = sm->foff[0][steps] * Z, nB = sm->foff[1][steps] * Z;
-    // 2. all fragments (charges 1..Z), any order -- they are sorted next
+    // 2. all fragments (charges 1..Z) straight into the sort arrays, padded with +inf to a power of two
+    const float PINF = __int_as_float(0x7f800000);
+    int NA = 32, NB = 32;
+    while (NA < nA) NA <<= 1;
+    while (NB < nB) NB <<= 1;
+    double a1, a2;
+    pa_type_consts(type, a1, a2);
     for (int w = 0; w < 2; w++) {
-        float* raw = w ? raw1 : raw0;
+        float* dst = w ? srt1 : srt0;
+        const int n = w ? nB : nA, N = w ? NB : NA;
+        for (int e = n + lane; e < N; e += 32) dst[e] = PINF;
         for (int step = lane; step < steps; step += 32) {
             const float run = sm->run[w][step];
             const int nls = sm->nls[w][step];
@@ -582,51 +673,68 @@ __device__ __forceinline__ void pa_sdi_type(const PaCfg& cfg, SelSmem* sm, const
             const int o = sm->foff[w][step] * Z;
             for (int v = 0; v < nv; v++) {
                 float base = cfg.has_nl ? __fsub_rn(run, __ldg(cfg.nl_sums + nls * 16 + v)) : run;
-                const double d = pa_type_adjust((double)base, type);
-                for (int z = 1; z <= Z; z++) raw[o + v * Z + (z - 1)] = pa_charge_mz(d, z);
+                const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
+                for (int z = 1; z <= Z; z++) dst[o + v * Z + (z - 1)] = pa_charge_mz(d, z);
             }
         }
     }
     __syncwarp();
-    // 3. sort both lists ascending (rank by counting; ties by index)
+    // 3. sort both lists ascending: warp-wide bitonic network over shared (or global) memory.
+    //    Only the sorted VALUES matter downstream, so any correct sort reproduces std::sort here.
     for (int w = 0; w < 2; w++) {
-        const float* raw = w ? raw1 : raw0;
-        float* srt = w ? srt1 : srt0;
-        const int n = w ? nB : nA;
-        for (int e = lane; e < n; e += 32) {
-            const float x = raw[e];
-            int pos = 0;
-            for (int j = 0; j < n; j++) { float y = raw[j]; pos += (y < x) || (y == x && j < e); }
-            srt[pos] = x;
+        float* arr = w ? srt1 : srt0;
+        const int N = w ? NB : NA;
+        for (int kk = 2; kk <= N; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (N >> 1); t += 32) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const bool asc = (i & kk) == 0;
+                    const float x = arr[i], y = arr[l];
+                    if ((x > y) == asc) { arr[i] = y; arr[l] = x; }
+                }
+                __syncwarp();
+            }
         }
     }
-    __syncwarp();
-    // 4. greedy tolerance merge (cpp/ModifiedPeptide.cpp:288-316) by lane 0; survivors are
-    //    compacted in place at the front of raw0 / raw1
-    int cA = 0, cB = 0;
+    // 4. greedy tolerance merge (cpp/ModifiedPeptide.cpp:288-316): sequential by nature, run by
+    //    lane 0 until one list is exhausted; the tail of the other list survives wholesale.
+    //    Survivors are compacted at the front of raw0 / raw1.
+    int cA = 0, cB = 0, ti = 0, tj = 0;
     if (lane == 0) {
         int i = 0, j = 0;
         const float err = cfg.err;
-        while (i < nA || j < nB) {
-            if (j == nB) raw0[cA++] = srt0[i++];
-            else if (i == nA) raw1[cB++] = srt1[j++];
-            else {
-                const float x = srt0[i], y = srt1[j];
-                if (fabsf(__fsub_rn(x, y)) < err) { i++; j++; }
-                else if (x < y) { raw0[cA++] = x; i++; }
-                else { raw1[cB++] = y; j++; }
+        float x = nA > 0 ? srt0[0] : PINF, y = nB > 0 ? srt1[0] : PINF;
+        while (i < nA && j < nB) {
+            if (fabsf(__fsub_rn(x, y)) < err) {
+                i++; j++;
+                x = i < nA ? srt0[i] : PINF;
+                y = j < nB ? srt1[j] : PINF;
+            } else if (x < y) {
+                raw0[cA++] = x; i++;
+                x = i < nA ? srt0[i] : PINF;
+            } else {
+                raw1[cB++] = y; j++;
+                y = j < nB ? srt1[j] : PINF;
             }
         }
+        ti = i; tj = j;
     }
     cA = __shfl_sync(PA_FULL, cA, 0);
     cB = __shfl_sync(PA_FULL, cB, 0);
+    ti = __shfl_sync(PA_FULL, ti, 0);
+    tj = __shfl_sync(PA_FULL, tj, 0);
+    for (int e = ti + lane; e < nA; e += 32) raw0[cA + (e - ti)] = srt0[e];
+    for (int e = tj + lane; e < nB; e += 32) raw1[cB + (e - tj)] = srt1[e];
+    cA += nA - ti;
+    cB += nB - tj;
     __syncwarp();
     // 5. hits: survivors whose matched rank <= depth
     int hA = 0, hB = 0;
     for (int e = lane; e < cA; e += 32)
-        hA += pa_match_rank(info.pm, info.pr, info.R, raw0[e], cfg.err, cfg.err_gt_half) <= depth;
+        hA += pa_match_rank(info, raw0[e], cfg.err, cfg.err_gt_half) <= depth;
     for (int e = lane; e < cB; e += 32)
-        hB += pa_match_rank(info.pm, info.pr, info.R, raw1[e], cfg.err, cfg.err_gt_half) <= depth;
+        hB += pa_match_rank(info, raw1[e], cfg.err, cfg.err_gt_half) <= depth;
     for (int o = 16; o > 0; o >>= 1) { hA += __shfl_xor_sync(PA_FULL, hA, o); hB += __shfl_xor_sync(PA_FULL, hB, o); }
     hitsA += hA; hitsB += hB; trialsA += cA; trialsB += cB;
     __syncwarp();
@@ -761,7 +869,7 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
         {
             // longest possible list of this PSM
             long long per_type = (long long)(info.L > 1 ? info.L - 1 : 1) * cfg.nvar_cap * info.Z;
-            if (per_type > PA_LCAP) {
+            if (per_type > PA_LCAP) {     // list_stride = power of two >= the chunk's longest list
                 float* g = a.g_lists + (size_t)gw * 4 * a.list_stride;
                 raw0 = g; raw1 = g + a.list_stride; srt0 = g + 2 * a.list_stride; srt1 = g + 3 * a.list_stride;
             }
@@ -774,7 +882,6 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
             rem &= rem - 1;
             // competitors: move the mod from `site` to each free site u
             float m = -INF;
-            uint64_t fs = free_sites;
             // pass 1: max competitor score
             for (int base = 0; base < 64; base += 32) {
                 int u = base + lane;
@@ -797,7 +904,6 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 }
                 tie |= (uint64_t)__ballot_sync(PA_FULL, is) << base;
             }
-            (void)fs;
             float asc = INF;
             uint64_t tt = tie;
             while (tt) {

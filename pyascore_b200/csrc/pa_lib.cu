@@ -569,9 +569,9 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     ba.bin_size = s->bin_size; ba.n_top = s->n_top;
     int cap = ((std::max(max_peaks, 32) + 31) / 32) * 32;
     cap = std::min(cap, 4096);
-    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / ((int64_t)cap * 20)));
+    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / (int64_t)PA_BIN_SLOT_BYTES(cap)));
     ba.cap = cap;
-    size_t smem = (size_t)wpb * cap * 20;
+    size_t smem = (size_t)wpb * PA_BIN_SLOT_BYTES(cap);
     int blocks = (int)std::min<int64_t>((ns + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
     cs.e_bin0 = next_event(s); cs.e_bin1 = next_event(s); cs.e_plan1 = next_event(s);
     CK(cudaEventRecord(cs.e_bin0, st));
@@ -663,8 +663,14 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         const int wpb = 8;
         int blocks = (int)std::min<int64_t>(((int64_t)n_units + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
         size_t smem = wpb * sizeof(PsmSmem);
-        if (s->cfg.has_nl) k_count_score<true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
-        else k_count_score<false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+        const bool pair = s->cfg.n_types == 2;
+        if (s->cfg.has_nl) {
+            if (pair) k_count_score<true, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+            else k_count_score<true, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+        } else {
+            if (pair) k_count_score<false, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+            else k_count_score<false, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+        }
         CK(cudaGetLastError());
         s->ctr.kernel_launches++; s->ctr.launches_count++;
     }
@@ -691,7 +697,8 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.psm_status_out = cs.o_status ? cs.o_status + r.p0 : nullptr;
         const int wpb = 8;
         int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * 2);
-        sa.list_stride = ((int64_t)std::max(T.max_list, 1) + 31) / 32 * 32;
+        sa.list_stride = 32;
+        while (sa.list_stride < T.max_list) sa.list_stride <<= 1;
         if (T.max_list > PA_LCAP) CK(sl.g_lists.ensure((size_t)blocks * wpb * 4 * sa.list_stride * sizeof(float)));
         sa.g_lists = sl.g_lists.as<float>();
         sa.g_sort = sl.g_sort.as<unsigned long long>();
@@ -749,7 +756,6 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
     // ---- chunking ----
     std::vector<ChunkRange> chunks;
     std::vector<int> chunk_maxp;
-    int64_t mod_total_lo = 0;
     std::vector<int64_t> mod_lo, mod_hi;
     if (in_dev || keep) {
         chunks.push_back({0, in->n_psm, 0, in->n_spec});
@@ -772,7 +778,6 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
             }
         }
     }
-    (void)mod_total_lo;
     for (auto& c : chunks) {
         int mp = 512;
         if (!in_dev) {
@@ -897,7 +902,8 @@ extern "C" int pa_calculate_ambiguity(pa_scorer* s, int64_t psm, uint64_t sig_a,
     memcpy(a.scA, scores_a, sizeof(a.scA)); memcpy(a.scB, scores_b, sizeof(a.scB));
     DevBuf d_out, d_lists;
     CK(d_out.ensure(4));
-    a.list_stride = ((int64_t)std::max(s->kept.max_list, 1) + 31) / 32 * 32;
+    a.list_stride = 32;
+    while (a.list_stride < s->kept.max_list) a.list_stride <<= 1;
     if (s->kept.max_list > PA_LCAP) CK(d_lists.ensure((size_t)4 * a.list_stride * sizeof(float)));
     a.g_lists = d_lists.as<float>(); a.out = d_out.as<float>();
     k_ambiguity<<<1, 32, sizeof(SelSmem)>>>(s->cfg, s->kept.b, a);
@@ -974,10 +980,10 @@ extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_
     ba.g_bin = sl.g_bin.as<int32_t>() - lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - lo;
     ba.rcount = sl.rcount.as<int32_t>(); ba.bin_size = s->bin_size; ba.n_top = s->n_top;
     int cap = (int)std::min<int64_t>(((std::max<int64_t>(m, 32) + 31) / 32) * 32, 4096);
-    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / ((int64_t)cap * 20)));
+    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / (int64_t)PA_BIN_SLOT_BYTES(cap)));
     ba.cap = cap;
     int blocks = (int)std::min<int64_t>((n_spec + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
-    k_bin_topn<<<blocks, wpb * 32, (size_t)wpb * cap * 20, st>>>(ba);
+    k_bin_topn<<<blocks, wpb * 32, (size_t)wpb * PA_BIN_SLOT_BYTES(cap), st>>>(ba);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_mz + lo, sl.rmz.p, (size_t)npk * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_rank + lo, sl.rrank.p, (size_t)npk, cudaMemcpyDeviceToHost, st));
