@@ -316,16 +316,17 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kern = {"bin_topn": ctr_dev["ms_bin"], "plan+scan": ctr_dev["ms_plan"], "count_score": ctr_dev["ms_count"],
-                "select_ascore": ctr_dev["ms_select"]}
-        dom = max(("bin_topn", "count_score", "select_ascore"), key=lambda k: kern[k])
+                "select": ctr_dev["ms_select"], "ascore": ctr_dev["ms_ascore"]}
+        dom = max(("bin_topn", "count_score", "select", "ascore"), key=lambda k: kern[k])
         n_launch = {"bin_topn": ctr_dev["launches_bin"], "count_score": ctr_dev["launches_count"],
-                    "select_ascore": ctr_dev["launches_select"]}[dom]
+                    "select": ctr_dev["launches_select"], "ascore": max(ctr_dev["launches_ascore"] // 2, 1)}[dom]
         peaks_n = int(batch["spec_off"][-1])
         # algorithmic bytes of each kernel's own stage per step (DESIGN.md section "kernels")
         retained = 5 * min(peaks_n, 10 * 20 * (batch["spec_off"].size - 1))
         alg = {"bin_topn": 16 * peaks_n + retained,
                "count_score": retained + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 12 * n_psm + 24 * int(ctr_dev["n_isoforms"]),
-               "select_ascore": retained + int(batch["pep_off"][-1]) + 24 * int(ctr_dev["n_isoforms"]) + 16 * n_psm + 12 * mod_total}
+               "select": 4 * int(ctr_dev["n_isoforms"]) + 28 * n_psm + 20 * mod_total,
+               "ascore": retained + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 16 * mod_total + 4 * mod_total}
         dom_ms = kern[dom] / max(n_launch, 1)
         achieved = alg[dom] / max(n_launch, 1) / (dom_ms * 1e-3) / 1e9
         step_alg = algorithmic_bytes(batch, mod_total)

@@ -144,7 +144,8 @@ typedef struct {
     int64_t bytes_h2d, bytes_d2h;      /* copied by the library during the last pa_score_batch */
     int64_t kernel_launches;           /* kernels launched by the last pa_score_batch */
     float ms_bin, ms_plan, ms_count, ms_select, ms_total; /* CUDA-event times, summed over chunks */
-    int64_t launches_bin, launches_count, launches_select;
+    int64_t launches_bin, launches_count, launches_select, launches_ascore;
+    float ms_ascore, reserved;          /* ms_select = best-isoform selection, ms_ascore = Ascore kernels */
 } pa_counters_t;
 
 /* Counters of the last pa_score_batch (roofline arithmetic: SURVEY.md section 8d). */

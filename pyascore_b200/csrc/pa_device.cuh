@@ -34,6 +34,9 @@ struct PaCfg {
     const uint32_t* binom;           // saturating C(n,k), [64*64]
     const float* nl_sums;            // [256][16] sorted distinct <=2-subset sums per capped-count state
     const uint8_t* nl_nvar;          // [256]
+    const float* res_tab;            // global copies of res_mass / nl_upper / nl_lower for per-lane gathers
+    const uint8_t* nl_up_tab;        // (kernel parameters sit in the constant bank: divergent indices serialise)
+    const uint8_t* nl_lo_tab;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -216,13 +219,13 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
         bool site = false;
         if (i < L) {
             int c = (int)b.pep[o + i] - 'A';
-            float m0 = (c >= 0 && c < 26) ? cfg.res_mass[c] : __int_as_float(0x7fc00000);
+            float m0 = (c >= 0 && c < 26) ? __ldg(cfg.res_tab + c) : __int_as_float(0x7fc00000);
             bool lett = (c >= 0 && c < 26) && ((cfg.mod_letters >> c) & 1u);
             site = lett || (cfg.allow_n && i == 0) || (cfg.allow_c && i == L - 1);
             sm->res[i][0] = m0;
             sm->res[i][1] = site ? __fadd_rn(m0, cfg.mod_mass) : 0.f;
             uint8_t n0 = 0, n1 = 0;
-            if (cfg.has_nl && c >= 0 && c < 26) { n0 = cfg.nl_upper[c]; n1 = site ? cfg.nl_lower[c] : 0; }
+            if (cfg.has_nl && c >= 0 && c < 26) { n0 = __ldg(cfg.nl_up_tab + c); n1 = site ? __ldg(cfg.nl_lo_tab + c) : 0; }
             sm->nlidx[i][0] = n0;
             sm->nlidx[i][1] = n1;
         }

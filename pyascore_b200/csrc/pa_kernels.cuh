@@ -521,9 +521,11 @@ struct PaSelArgs {
     uint64_t* alt_sites;
     int32_t* psm_status_out;
     // scratch
-    float* g_lists;              // per warp 4 * list_stride floats, when a list exceeds PA_LCAP
-    int64_t list_stride;
     unsigned long long* g_sort;  // per isoform (iso_off), for std::sort emulation beyond PA_SORTCAP
+    int64_t mod_lo;              // absolute index of the chunk's first mod entry
+    uint32_t* best_idx;          // [n_psm] best isoform (lexicographic rank), 0xffffffff = none
+    int32_t* mod_psm;            // [entries] chunk-relative PSM of each mod entry, -1 = no Ascore to compute
+    unsigned long long* tie;     // [entries] tied best competitors of each mod entry
 };
 
 // --- libstdc++ std::sort (introsort + final insertion sort), comparator a.w > b.w ------------
@@ -770,10 +772,13 @@ __device__ __forceinline__ void pa_depth_scores(const PaCfg& cfg, unsigned long 
     for (int d = 0; d < PA_N_TOP; d++) sc[d] = __ldg(cfg.T + pa_tab_index(n, pa_cum_get(lo, hi, d), d));
 }
 
+// K3a: warp per PSM.  Best isoform in the reference's order + per modified site the set of tied
+// best competitors (= alternative sites).  The Ascore of every (PSM, site) entry is then computed
+// by k_ascore (thread per entry) or, for the rare shapes that kernel does not cover, k_ascore_generic.
 __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    SelSmem* sm = (SelSmem*)smem_raw + wib;
+    unsigned long long* s_sort = (unsigned long long*)smem_raw + (size_t)wib * PA_SORTCAP;
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const float INF = __int_as_float(0x7f800000);
 
@@ -789,28 +794,22 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
             if (a.n_iso) a.n_iso[p] = I;
             if (a.n_sites) a.n_sites[p] = S;
         }
-        if (status != PA_PSM_OK || I == 0) {
-            // no isoform: best_sequence "" / best_score -1 (cpp/Ascore.cpp:273-295); k > #sites is
-            // "unambiguous" there (ascores inf); errors report NaN
-            const float fill = (status == PA_PSM_OK) ? INF : __int_as_float(0x7fc00000);
+        if (status != PA_PSM_OK || I == 0 || k >= S) {
+            // no isoform: best_sequence "" / best_score -1 (cpp/Ascore.cpp:273-295); k >= #sites is
+            // "unambiguous" (cpp/Ascore.cpp:38-51: ascores inf, no alternatives); errors report NaN
+            const bool ok = status == PA_PSM_OK;
+            const float fill = ok ? INF : __int_as_float(0x7fc00000);
             if (lane == 0) {
-                if (a.best_sig) a.best_sig[p] = 0;
-                if (a.best_score) a.best_score[p] = (status == PA_PSM_OK) ? -1.f : fill;
+                uint64_t sig = 0; float sc = ok ? -1.f : fill;
+                if (ok && I > 0) { sig = (S >= 64) ? ~0ull : ((1ull << S) - 1ull); sc = a.iso.w[ib]; }
+                if (a.best_sig) a.best_sig[p] = sig;
+                if (a.best_score) a.best_score[p] = sc;
+                a.best_idx[p] = (ok && I > 0) ? 0u : 0xffffffffu;
             }
             for (int j = lane; j < k; j += 32) {
                 if (a.ascores) a.ascores[mo + j] = fill;
                 if (a.alt_sites) a.alt_sites[mo + j] = 0;
-            }
-            continue;
-        }
-        if (k >= S) {   // exactly one isoform, unambiguous (cpp/Ascore.cpp:38-51)
-            if (lane == 0) {
-                if (a.best_sig) a.best_sig[p] = (S >= 64) ? ~0ull : ((1ull << S) - 1ull);
-                if (a.best_score) a.best_score[p] = a.iso.w[ib];
-            }
-            for (int j = lane; j < k; j += 32) {
-                if (a.ascores) a.ascores[mo + j] = INF;
-                if (a.alt_sites) a.alt_sites[mo + j] = 0;
+                a.mod_psm[mo + j - a.mod_lo] = -1;
             }
             continue;
         }
@@ -838,7 +837,7 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 unsigned bal = __ballot_sync(PA_FULL, is);
                 best = __shfl_sync(PA_FULL, id, __ffs(bal) - 1);
             } else {
-                unsigned long long* arr = (I <= PA_SORTCAP) ? (unsigned long long*)&sm->raw[0][0] : a.g_sort + ib;
+                unsigned long long* arr = (I <= PA_SORTCAP) ? s_sort : a.g_sort + ib;
                 __syncwarp();
                 for (int64_t q = lane; q < I; q += 32) {
                     uint32_t id = perm[q];
@@ -853,75 +852,356 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
             }
         }
         const uint64_t best_bits = pa_unrank(cfg.binom, S, k, best);
-        const float wbest = a.iso.w[ib + best];
         if (lane == 0) {
             if (a.best_sig) a.best_sig[p] = best_bits;
-            if (a.best_score) a.best_score[p] = wbest;
+            if (a.best_score) a.best_score[p] = a.iso.w[ib + best];
+            a.best_idx[p] = best;
         }
-        if (a.ascores == nullptr && a.alt_sites == nullptr) continue;
-
-        // ---- Ascores ---------------------------------------------------------------------
-        PsmInfo info;
-        pa_setup_psm(cfg, b, p, &sm->psm, info, true);
-        float scBest[PA_N_TOP];
-        pa_depth_scores(cfg, a.iso.lo[ib + best], a.iso.hi[ib + best], (int)a.iso.nfrag[ib + best], scBest);
-        float* raw0 = sm->raw[0]; float* raw1 = sm->raw[1]; float* srt0 = sm->srt[0]; float* srt1 = sm->srt[1];
-        {
-            // longest possible list of this PSM
-            long long per_type = (long long)(info.L > 1 ? info.L - 1 : 1) * cfg.nvar_cap * info.Z;
-            if (per_type > PA_LCAP) {     // list_stride = power of two >= the chunk's longest list
-                float* g = a.g_lists + (size_t)gw * 4 * a.list_stride;
-                raw0 = g; raw1 = g + a.list_stride; srt0 = g + 2 * a.list_stride; srt1 = g + 3 * a.list_stride;
-            }
-        }
+        // ---- tied best competitors per modified site (cpp/Ascore.cpp:212-254) ---------------
         const uint64_t all = (S >= 64) ? ~0ull : ((1ull << S) - 1ull);
         const uint64_t free_sites = all & ~best_bits;
         uint64_t rem = best_bits;
         for (int j = 0; j < k; j++) {
             const int site = __ffsll((long long)rem) - 1;
             rem &= rem - 1;
-            // competitors: move the mod from `site` to each free site u
-            float m = -INF;
-            // pass 1: max competitor score
-            for (int base = 0; base < 64; base += 32) {
-                int u = base + lane;
-                float w = -INF;
-                if (u < S && ((free_sites >> u) & 1ull)) {
-                    uint64_t cb = (best_bits & ~(1ull << site)) | (1ull << u);
-                    w = a.iso.w[ib + pa_rank(cfg.binom, S, k, cb)];
-                }
-                m = w > m ? w : m;
-            }
+            float w0 = -INF, w1 = -INF;      // competitor scores of free sites lane, lane+32
+            if (lane < S && ((free_sites >> lane) & 1ull))
+                w0 = a.iso.w[ib + pa_rank(cfg.binom, S, k, (best_bits & ~(1ull << site)) | (1ull << lane))];
+            if (lane + 32 < S && ((free_sites >> (lane + 32)) & 1ull))
+                w1 = a.iso.w[ib + pa_rank(cfg.binom, S, k, (best_bits & ~(1ull << site)) | (1ull << (lane + 32)))];
+            float m = w0 > w1 ? w0 : w1;
             for (int o = 16; o > 0; o >>= 1) { float t = __shfl_xor_sync(PA_FULL, m, o); m = t > m ? t : m; }
-            // pass 2: tie set
-            uint64_t tie = 0;
-            for (int base = 0; base < 64; base += 32) {
-                int u = base + lane;
-                bool is = false;
-                if (u < S && ((free_sites >> u) & 1ull)) {
-                    uint64_t cb = (best_bits & ~(1ull << site)) | (1ull << u);
-                    is = a.iso.w[ib + pa_rank(cfg.binom, S, k, cb)] == m;
-                }
-                tie |= (uint64_t)__ballot_sync(PA_FULL, is) << base;
-            }
-            float asc = INF;
-            uint64_t tt = tie;
-            while (tt) {
-                const int u = __ffsll((long long)tt) - 1;
-                tt &= tt - 1;
-                const uint64_t cb = (best_bits & ~(1ull << site)) | (1ull << u);
-                const uint32_t ci = pa_rank(cfg.binom, S, k, cb);
-                float scC[PA_N_TOP];
-                pa_depth_scores(cfg, a.iso.lo[ib + ci], a.iso.hi[ib + ci], (int)a.iso.nfrag[ib + ci], scC);
-                const float amb = pa_ambiguity(cfg, sm, info, best_bits, scBest, wbest, cb, scC, a.iso.w[ib + ci],
-                                               raw0, raw1, srt0, srt1);
-                asc = amb < asc ? amb : asc;
-            }
+            const bool f0 = lane < S && ((free_sites >> lane) & 1ull) && w0 == m;
+            const bool f1 = lane + 32 < S && ((free_sites >> (lane + 32)) & 1ull) && w1 == m;
+            const uint64_t tie = (uint64_t)__ballot_sync(PA_FULL, f0) | ((uint64_t)__ballot_sync(PA_FULL, f1) << 32);
             if (lane == 0) {
-                if (a.ascores) a.ascores[mo + j] = asc;
                 if (a.alt_sites) a.alt_sites[mo + j] = tie;
+                a.tie[mo + j - a.mod_lo] = tie;
+                a.mod_psm[mo + j - a.mod_lo] = (int32_t)p;
             }
         }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: one THREAD per (PSM, modified site) entry.  For every tied competitor: the site-determining
+// ion comparison of cpp/Ascore.cpp:157-210 + cpp/ModifiedPeptide.cpp:259-320, computed without
+// materialising or sorting the fragment lists: each (charge, neutral-loss variant) is a stream that
+// is already ascending along the peptide, so "sort, then tolerance-merge" becomes a k-way streaming
+// merge whose element VALUES are exactly those of the reference's sorted lists.  If a stream is
+// ever found non-ascending (non-positive residue mass), or the shape is out of range (too many
+// streams, one-residue peptide), the entry is queued for k_ascore_generic instead.
+// ---------------------------------------------------------------------------------------------
+#define PA_MAXSTREAM 12
+
+struct PaAscArgs {
+    int64_t n_entries;           // mod entries of this chunk
+    int64_t mod_lo;              // absolute index of the chunk's first entry
+    const int32_t* mod_psm;      // [n_entries] chunk-relative PSM, -1 = nothing to do
+    const unsigned long long* tie;   // [n_entries] tied competitor sites
+    const uint32_t* best_idx;    // [n_psm]
+    const int64_t* mod_off;      // [n_psm+1] absolute
+    const int64_t* iso_off;
+    const int32_t* psm_S;
+    PaIso iso;
+    float* ascores;              // absolute-indexed output (may be null)
+    int32_t* generic_list;       // entries that need the generic kernel
+    int* generic_count;
+};
+
+struct AscPep {                  // what a thread needs to know about its peptide
+    const uint8_t* pep;
+    int L, Z, a0, a1;
+    const uint32_t* aux_pos;
+    const float* aux_mass;
+};
+
+// residue mass / neutral-loss index of residue i in modification state st
+// (cpp/ModifiedPeptide.cpp:24-79 evaluated on the fly instead of tabulated)
+__device__ __forceinline__ float asc_res(const PaCfg& cfg, const AscPep& q, int i, int st, int& nlidx) {
+    const int c = (int)q.pep[i] - 'A';
+    float m = __ldg(cfg.res_tab + c);
+    if (st) m = __fadd_rn(m, cfg.mod_mass);
+    nlidx = 0;
+    if (cfg.has_nl) nlidx = st ? __ldg(cfg.nl_lo_tab + c) : __ldg(cfg.nl_up_tab + c);
+    for (int a = q.a0; a < q.a1; a++) {
+        const uint32_t pos = q.aux_pos[a];
+        const int idx = pos > 0 ? (int)pos - 1 : 0;
+        if (idx == i) {
+            m = __fadd_rn(m, q.aux_mass[a]);
+            if (cfg.has_nl && __ldg(cfg.nl_lo_tab + c)) nlidx = __ldg(cfg.nl_lo_tab + c);
+        }
+    }
+    return m;
+}
+
+struct AscList {                 // streams of one isoform for one ion type
+    float run[PA_MAXSTREAM];
+    float val[PA_MAXSTREAM];
+    float sigma[PA_MAXSTREAM];
+    short step[PA_MAXSTREAM];
+    short zq[PA_MAXSTREAM];
+    int nq;                      // number of streams
+    int left;                    // elements not yet popped
+};
+
+// returns false when the shape is not supported by the streaming formulation
+__device__ __forceinline__ bool asc_init(const PaCfg& cfg, const AscPep& q, uint64_t mlo, uint64_t mhi, bool fwd,
+                                         double a1, double a2, AscList& ls) {
+    const int L = q.L, Z = q.Z, steps = L - 1;
+    float sig[PA_MAXSTREAM], run_at[PA_MAXSTREAM];
+    short start[PA_MAXSTREAM];
+    int V = 1;
+    if (!cfg.has_nl) {
+        // one stream per charge: no loss (sigma 0), present from the first residue on
+        if (Z > PA_MAXSTREAM) return false;
+        const int i = fwd ? 0 : L - 1;
+        const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+        int idx;
+        sig[0] = 0.f; start[0] = 0;
+        run_at[0] = asc_res(cfg, q, i, st, idx);
+    } else {
+        // pass 1: the final neutral-loss state says which sums will ever exist
+        int nls = 0;
+        for (int step = 0; step < steps; step++) {
+            const int i = fwd ? step : L - 1 - step;
+            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+            int idx;
+            (void)asc_res(cfg, q, i, st, idx);
+            if (idx) nls = pa_nl_bump(nls, idx);
+        }
+        V = cfg.nl_nvar[nls];
+        if (V * Z > PA_MAXSTREAM) return false;
+        for (int v = 0; v < V; v++) { sig[v] = __ldg(cfg.nl_sums + nls * 16 + v); start[v] = -1; run_at[v] = 0.f; }
+        // pass 2: the step at which each sum first becomes available (the stack only grows, so
+        // it stays available afterwards) and the running sum there
+        int started = 0;
+        float run = 0.f;
+        nls = 0;
+        for (int step = 0; step < steps && started < V; step++) {
+            const int i = fwd ? step : L - 1 - step;
+            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+            int idx;
+            const float r = asc_res(cfg, q, i, st, idx);
+            run = (step == 0) ? r : __fadd_rn(r, run);
+            const int before = nls;
+            if (idx) nls = pa_nl_bump(nls, idx);
+            if (step == 0 || nls != before) {
+                const int nv = cfg.nl_nvar[nls];
+                for (int v = 0; v < V; v++) {
+                    if (start[v] >= 0) continue;
+                    bool in = false;
+                    for (int u = 0; u < nv; u++) in |= (__ldg(cfg.nl_sums + nls * 16 + u) == sig[v]);
+                    if (in) { start[v] = (short)step; run_at[v] = run; started++; }
+                }
+            }
+        }
+    }
+    ls.nq = 0; ls.left = 0;
+    for (int v = 0; v < V; v++) {
+        if (cfg.has_nl && start[v] < 0) continue;     // cannot happen: every final sum appears somewhere
+        for (int z = 1; z <= Z; z++) {
+            const int qi = ls.nq++;
+            ls.run[qi] = run_at[v]; ls.sigma[qi] = sig[v]; ls.step[qi] = start[v]; ls.zq[qi] = (short)z;
+            const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run_at[v], sig[v]), a1), a2);
+            ls.val[qi] = pa_charge_mz(d, z);
+            ls.left += steps - start[v];
+        }
+    }
+    return true;
+}
+
+// pop the smallest pending fragment of the list; `mono` is cleared if a stream ever decreases
+__device__ __forceinline__ float asc_pop(const PaCfg& cfg, const AscPep& q, uint64_t mlo, uint64_t mhi, bool fwd,
+                                         double a1, double a2, AscList& ls, bool& mono) {
+    int bq = 0;
+    float x = ls.val[0];
+    for (int i = 1; i < ls.nq; i++) { const float v = ls.val[i]; if (v < x) { x = v; bq = i; } }
+    const int L = q.L, steps = L - 1;
+    const int step = ls.step[bq] + 1;
+    ls.step[bq] = (short)step;
+    ls.left--;
+    if (step < steps) {
+        const int i = fwd ? step : L - 1 - step;
+        const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+        int idx;
+        const float r = asc_res(cfg, q, i, st, idx);
+        const float run = __fadd_rn(r, ls.run[bq]);
+        ls.run[bq] = run;
+        const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run, ls.sigma[bq]), a1), a2);
+        const float nv = pa_charge_mz(d, ls.zq[bq]);
+        if (nv < x) mono = false;
+        ls.val[bq] = nv;
+    } else ls.val[bq] = __int_as_float(0x7f800000);
+    return x;
+}
+
+__device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int R, float f, float err, int err_gt_half) {
+    const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
+    int a = 0, n = R;
+    while (n > 0) {
+        int h = n >> 1;
+        if (!(__ldg(pm + a + h) > lo)) { a += h + 1; n -= h + 1; } else n = h;
+    }
+    int best = 255;
+    for (; a < R; a++) {
+        const float p = __ldg(pm + a);
+        if (!(p < hi)) break;
+        if (err_gt_half && !((double)f >= (double)p - .5)) continue;
+        const int r = __ldg(pr + a);
+        best = r < best ? r : best;
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_entries) return;
+    const int32_t p = a.mod_psm[t];
+    if (p < 0) return;
+    const int j = (int)(a.mod_lo + t - a.mod_off[p]);
+    const int S = a.psm_S[p], k = b.n_mod[p];
+    const int64_t ib = a.iso_off[p];
+    AscPep q;
+    const int po = b.pep_off[p];
+    q.pep = b.pep + po; q.L = b.pep_off[p + 1] - po; q.Z = b.max_charge[p];
+    q.a0 = 0; q.a1 = 0; q.aux_pos = b.aux_pos; q.aux_mass = b.aux_mass;
+    if (b.aux_off != nullptr) { q.a0 = b.aux_off[p]; q.a1 = b.aux_off[p + 1]; }
+    const int sp = b.psm_spec[p];
+    const int64_t off = b.spec_off[sp] - b.spec_base;
+    const float* pm = b.rmz + off;
+    const uint8_t* pr = b.rrank + off;
+    const int R = b.rcount[sp];
+
+    const uint32_t best = a.best_idx[p];
+    const uint64_t best_bits = pa_unrank(cfg.binom, S, k, best);
+    uint64_t rem = best_bits;
+    for (int jj = 0; jj < j; jj++) rem &= rem - 1;
+    const int site = __ffsll((long long)rem) - 1;
+    // site index -> residue position (sites are the modifiable residues N->C)
+    int site_res[64];
+    {
+        int n = 0;
+        for (int i = 0; i < q.L && n < 64; i++) {
+            const int c = (int)q.pep[i] - 'A';
+            const bool is = ((cfg.mod_letters >> c) & 1u) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == q.L - 1);
+            if (is) site_res[n++] = i;
+        }
+    }
+    uint64_t alo = 0, ahi = 0;
+    for (uint64_t bb = best_bits; bb; bb &= bb - 1) {
+        const int pos = site_res[__ffsll((long long)bb) - 1];
+        if (pos < 64) alo |= 1ull << pos; else ahi |= 1ull << (pos - 64);
+    }
+    float scA[PA_N_TOP];
+    pa_depth_scores(cfg, a.iso.lo[ib + best], a.iso.hi[ib + best], (int)a.iso.nfrag[ib + best], scA);
+    const float wA = a.iso.w[ib + best];
+
+    bool generic = (q.L < 2);
+    float asc = __int_as_float(0x7f800000);
+    for (uint64_t tt = a.tie[t]; tt && !generic; tt &= tt - 1) {
+        const int u = __ffsll((long long)tt) - 1;
+        const uint64_t cb = (best_bits & ~(1ull << site)) | (1ull << u);
+        const uint32_t ci = pa_rank(cfg.binom, S, k, cb);
+        const float wB = a.iso.w[ib + ci];
+        float amb = 0.f;
+        if (!((double)fabsf(__fsub_rn(wA, wB)) < 1e-6)) {
+            float scB[PA_N_TOP];
+            pa_depth_scores(cfg, a.iso.lo[ib + ci], a.iso.hi[ib + ci], (int)a.iso.nfrag[ib + ci], scB);
+            float max_diff = 0.f;
+            int depth = 0;
+#pragma unroll
+            for (int d = 0; d < PA_N_TOP; d++) {
+                const float diff = __fsub_rn(scA[d], scB[d]);
+                if (diff > max_diff) { max_diff = diff; depth = d; }
+            }
+            // competitor mask = best mask with the mod moved from `site` to site u
+            uint64_t blo = alo, bhi = ahi;
+            { const int pos = site_res[site]; if (pos < 64) blo &= ~(1ull << pos); else bhi &= ~(1ull << (pos - 64)); }
+            { const int pos = site_res[u]; if (pos < 64) blo |= 1ull << pos; else bhi |= 1ull << (pos - 64); }
+            int hitsA = 0, hitsB = 0, trialsA = 0, trialsB = 0;
+            for (int ti = 0; ti < cfg.n_types && !generic; ti++) {
+                const char type = cfg.types[ti];
+                const bool fwd = (type == 'b' || type == 'c');
+                double a1, a2;
+                pa_type_consts(type, a1, a2);
+                AscList A, B;
+                if (!asc_init(cfg, q, alo, ahi, fwd, a1, a2, A) || !asc_init(cfg, q, blo, bhi, fwd, a1, a2, B)) { generic = true; break; }
+                bool mono = true;
+                float x = 0.f, y = 0.f;
+                bool hx = false, hy = false;         // a popped element is pending
+                // greedy tolerance merge of cpp/ModifiedPeptide.cpp:288-316 over the two streams
+                for (;;) {
+                    if (!hx && A.left > 0) { x = asc_pop(cfg, q, alo, ahi, fwd, a1, a2, A, mono); hx = true; }
+                    if (!hy && B.left > 0) { y = asc_pop(cfg, q, blo, bhi, fwd, a1, a2, B, mono); hy = true; }
+                    if (!hx && !hy) break;
+                    if (!hy) { trialsA++; hitsA += asc_match(pm, pr, R, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
+                    else if (!hx) { trialsB++; hitsB += asc_match(pm, pr, R, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
+                    else if (fabsf(__fsub_rn(x, y)) < cfg.err) { hx = false; hy = false; }
+                    else if (x < y) { trialsA++; hitsA += asc_match(pm, pr, R, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
+                    else { trialsB++; hitsB += asc_match(pm, pr, R, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
+                }
+                if (!mono) generic = true;
+            }
+            if (!generic) {
+                const float sA = __ldg(cfg.T + pa_tab_index(trialsA, hitsA, depth));
+                const float sB = __ldg(cfg.T + pa_tab_index(trialsB, hitsB, depth));
+                amb = __fsub_rn(sA, sB);
+            }
+        }
+        asc = amb < asc ? amb : asc;
+    }
+    if (generic) {
+        const int slot = atomicAdd(a.generic_count, 1);
+        a.generic_list[slot] = (int32_t)t;
+        return;
+    }
+    if (a.ascores) a.ascores[a.mod_lo + t] = asc;
+}
+
+// K3c: generic (warp-cooperative, list-materialising) Ascore for the entries k_ascore queued.
+__global__ void __launch_bounds__(256) k_ascore_generic(PaCfg cfg, PaBatchDev b, PaAscArgs a, float* g_lists,
+                                                         int64_t list_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    SelSmem* sm = (SelSmem*)smem_raw + wib;
+    const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
+    const int n = *a.generic_count;
+    for (int64_t e = gw; e < n; e += nw) {
+        const int64_t t = a.generic_list[e];
+        const int32_t p = a.mod_psm[t];
+        const int j = (int)(a.mod_lo + t - a.mod_off[p]);
+        const int S = a.psm_S[p], k = b.n_mod[p];
+        const int64_t ib = a.iso_off[p];
+        PsmInfo info;
+        pa_setup_psm(cfg, b, p, &sm->psm, info, true);
+        const uint32_t best = a.best_idx[p];
+        const uint64_t best_bits = pa_unrank(cfg.binom, S, k, best);
+        uint64_t rem = best_bits;
+        for (int jj = 0; jj < j; jj++) rem &= rem - 1;
+        const int site = __ffsll((long long)rem) - 1;
+        float scBest[PA_N_TOP];
+        pa_depth_scores(cfg, a.iso.lo[ib + best], a.iso.hi[ib + best], (int)a.iso.nfrag[ib + best], scBest);
+        const float wbest = a.iso.w[ib + best];
+        float* raw0 = sm->raw[0]; float* raw1 = sm->raw[1]; float* srt0 = sm->srt[0]; float* srt1 = sm->srt[1];
+        long long per_type = (long long)(info.L > 1 ? info.L - 1 : 1) * cfg.nvar_cap * info.Z;
+        if (per_type > PA_LCAP) {     // list_stride = power of two >= the chunk's longest list
+            float* g = g_lists + (size_t)gw * 4 * list_stride;
+            raw0 = g; raw1 = g + list_stride; srt0 = g + 2 * list_stride; srt1 = g + 3 * list_stride;
+        }
+        float asc = __int_as_float(0x7f800000);
+        for (uint64_t tt = a.tie[t]; tt; tt &= tt - 1) {
+            const int u = __ffsll((long long)tt) - 1;
+            const uint64_t cb = (best_bits & ~(1ull << site)) | (1ull << u);
+            const uint32_t ci = pa_rank(cfg.binom, S, k, cb);
+            float scC[PA_N_TOP];
+            pa_depth_scores(cfg, a.iso.lo[ib + ci], a.iso.hi[ib + ci], (int)a.iso.nfrag[ib + ci], scC);
+            const float amb = pa_ambiguity(cfg, sm, info, best_bits, scBest, wbest, cb, scC, a.iso.w[ib + ci],
+                                           raw0, raw1, srt0, srt1);
+            asc = amb < asc ? amb : asc;
+        }
+        if (lane == 0 && a.ascores) a.ascores[a.mod_lo + t] = asc;
         __syncwarp();
     }
 }

@@ -60,7 +60,7 @@ struct Slot {                // per-stream working set
     // plan
     DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
     // K2/K3
-    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups;
+    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, best_idx, mod_psm, tie, generic_list, generic_count;
     // staged outputs
     DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
     PlanTotals* h_totals = nullptr;      // pinned
@@ -70,7 +70,7 @@ struct Slot {                // per-stream working set
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rmz, &rrank, &rcount, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lists, &lookups, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lists, &lookups, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_totals) cudaFreeHost(h_totals);
@@ -106,7 +106,7 @@ struct pa_scorer {
     std::vector<float> nl_values;          // distinct non-zero loss masses, index+1 = device index
     bool nl_dirty = true;
     PaCfg cfg;
-    DevBuf d_T, d_logd, d_binom, d_nl_sums, d_nl_nvar, d_perm_pool, d_perm_off;
+    DevBuf d_T, d_logd, d_binom, d_nl_sums, d_nl_nvar, d_perm_pool, d_perm_off, d_lut;
     int table_n = -1;
     float lps[PA_N_TOP], lpf[PA_N_TOP];
     std::vector<int64_t> perm_off;         // [64*64]
@@ -241,6 +241,17 @@ static int refresh_config(pa_scorer* s) {
         CK(cudaMemcpy(s->d_nl_sums.p, sums.data(), sums.size() * sizeof(float), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(s->d_nl_nvar.p, nvar.data(), nvar.size(), cudaMemcpyHostToDevice));
         s->nl_dirty = false;
+    }
+    {   // global copies of the small per-letter tables (gathered per lane in the kernels)
+        unsigned char lut[26 * 4 + 52];
+        memcpy(lut, c.res_mass, 26 * 4);
+        memcpy(lut + 104, c.nl_upper, 26);
+        memcpy(lut + 130, c.nl_lower, 26);
+        CK(s->d_lut.ensure(sizeof(lut)));
+        CK(cudaMemcpy(s->d_lut.p, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        c.res_tab = s->d_lut.as<float>();
+        c.nl_up_tab = s->d_lut.as<uint8_t>() + 104;
+        c.nl_lo_tab = s->d_lut.as<uint8_t>() + 130;
     }
     c.nl_sums = s->d_nl_sums.as<float>();
     c.nl_nvar = s->d_nl_nvar.as<uint8_t>();
@@ -425,7 +436,7 @@ extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float
             CK(cudaMallocHost(&s->slot[i].h_lookups, sizeof(unsigned long long)));
             CK(cudaEventCreateWithFlags(&s->slot[i].ev_plan, cudaEventDisableTiming));
         }
-        CK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ascore_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_bin_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_tail_table, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(k_ambiguity, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -459,7 +470,7 @@ extern "C" void pa_destroy(pa_scorer* s) {
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) s->slot[i].release();
     s->d_T.release(); s->d_logd.release(); s->d_binom.release(); s->d_nl_sums.release(); s->d_nl_nvar.release();
-    s->d_perm_pool.release(); s->d_perm_off.release();
+    s->d_perm_pool.release(); s->d_perm_off.release(); s->d_lut.release();
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     delete s;
 }
@@ -506,7 +517,7 @@ struct ChunkState {              // what the back half of a chunk needs from the
     PaBatchDev b;
     int64_t mod_lo = 0, mod_hi = 0;
     const int64_t* mod_off_abs = nullptr;
-    cudaEvent_t e_bin0, e_bin1, e_plan1, e_cnt0, e_cnt1, e_sel1;
+    cudaEvent_t e_bin0, e_bin1, e_plan1, e_cnt0, e_cnt1, e_sel1, e_asc1;
     uint64_t* o_sig; float* o_score; int64_t* o_niso; int32_t* o_nsites; float* o_asc; uint64_t* o_alt; int32_t* o_status;
 };
 
@@ -683,6 +694,14 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     CK(stage_out(sl.o_asc, out->ascores, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, &cs.o_asc));
     CK(stage_out(sl.o_alt, out->alt_sites, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, &cs.o_alt));
     CK(stage_out(sl.o_status, out->psm_status, out_dev, r.p0, np, &cs.o_status));
+    const int64_t nm = cs.mod_hi - cs.mod_lo;
+    CK(sl.best_idx.ensure((size_t)std::max<int64_t>(np, 1) * 4));
+    CK(sl.mod_psm.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
+    CK(sl.tie.ensure((size_t)std::max<int64_t>(nm, 1) * 8));
+    CK(sl.generic_list.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
+    CK(sl.generic_count.ensure(4));
+    CK(cudaMemsetAsync(sl.generic_count.p, 0, 4, st));
+    cs.e_asc1 = next_event(s);
     if (np > 0) {
         PaSelArgs sa;
         sa.n_psm = np; sa.iso_off = sl.iso_off.as<int64_t>(); sa.psm_S = sl.psm_S.as<int32_t>();
@@ -695,18 +714,35 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.n_sites = cs.o_nsites ? cs.o_nsites + r.p0 : nullptr;
         sa.ascores = cs.o_asc; sa.alt_sites = cs.o_alt;            // indexed with absolute mod_off
         sa.psm_status_out = cs.o_status ? cs.o_status + r.p0 : nullptr;
-        const int wpb = 8;
-        int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * 2);
-        sa.list_stride = 32;
-        while (sa.list_stride < T.max_list) sa.list_stride <<= 1;
-        if (T.max_list > PA_LCAP) CK(sl.g_lists.ensure((size_t)blocks * wpb * 4 * sa.list_stride * sizeof(float)));
-        sa.g_lists = sl.g_lists.as<float>();
         sa.g_sort = sl.g_sort.as<unsigned long long>();
-        k_select<<<blocks, wpb * 32, wpb * sizeof(SelSmem), st>>>(s->cfg, cs.b, sa);
+        sa.mod_lo = cs.mod_lo; sa.best_idx = sl.best_idx.as<uint32_t>(); sa.mod_psm = sl.mod_psm.as<int32_t>();
+        sa.tie = sl.tie.as<unsigned long long>();
+        const int wpb = 8;
+        int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
+        k_select<<<blocks, wpb * 32, wpb * PA_SORTCAP * sizeof(unsigned long long), st>>>(s->cfg, cs.b, sa);
         CK(cudaGetLastError());
         s->ctr.kernel_launches++; s->ctr.launches_select++;
     }
     CK(cudaEventRecord(cs.e_sel1, st));
+    if (np > 0 && nm > 0 && cs.o_asc != nullptr) {
+        PaAscArgs aa;
+        aa.n_entries = nm; aa.mod_lo = cs.mod_lo; aa.mod_psm = sl.mod_psm.as<int32_t>();
+        aa.tie = sl.tie.as<unsigned long long>(); aa.best_idx = sl.best_idx.as<uint32_t>();
+        aa.mod_off = cs.mod_off_abs; aa.iso_off = sl.iso_off.as<int64_t>(); aa.psm_S = sl.psm_S.as<int32_t>();
+        aa.iso = iso; aa.ascores = cs.o_asc; aa.generic_list = sl.generic_list.as<int32_t>();
+        aa.generic_count = sl.generic_count.as<int>();
+        k_ascore<<<(unsigned)((nm + 127) / 128), 128, 0, st>>>(s->cfg, cs.b, aa);
+        CK(cudaGetLastError());
+        const int wpb = 8;
+        int blocks = s->sm_count * 2;
+        int64_t stride = 32;
+        while (stride < T.max_list) stride <<= 1;
+        if (T.max_list > PA_LCAP) CK(sl.g_lists.ensure((size_t)blocks * wpb * 4 * stride * sizeof(float)));
+        k_ascore_generic<<<blocks, wpb * 32, wpb * sizeof(SelSmem), st>>>(s->cfg, cs.b, aa, sl.g_lists.as<float>(), stride);
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches += 2; s->ctr.launches_ascore += 2;
+    }
+    CK(cudaEventRecord(cs.e_asc1, st));
     int64_t* d2h = &s->ctr.bytes_d2h;
     CK(copy_out(sl.o_sig, out->best_sig, out_dev, r.p0, np, st, d2h));
     CK(copy_out(sl.o_score, out->best_score, out_dev, r.p0, np, st, d2h));
@@ -831,6 +867,7 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
         cudaEventElapsedTime(&ms, cs[c].e_bin1, cs[c].e_plan1); s->ctr.ms_plan += ms;
         cudaEventElapsedTime(&ms, cs[c].e_cnt0, cs[c].e_cnt1); s->ctr.ms_count += ms;
         cudaEventElapsedTime(&ms, cs[c].e_cnt1, cs[c].e_sel1); s->ctr.ms_select += ms;
+        cudaEventElapsedTime(&ms, cs[c].e_sel1, cs[c].e_asc1); s->ctr.ms_ascore += ms;
     }
     cudaEventElapsedTime(&s->ctr.ms_total, e_all0, e_all1);
     s->ctr.n_fragment_lookups = (int64_t)(*s->slot[0].h_lookups) + (int64_t)(*s->slot[1].h_lookups);
