@@ -166,7 +166,7 @@ struct PsmSmem {
     uint8_t site_pos[64];         // residue index of site j
     float pm[PA_RCAP + 1];        // retained peaks, (float)mz ascending
     uint8_t pr[PA_RCAP + 1];      // their ranks
-    uint8_t cell[PA_NCELL];       // cell[c] = index of the first peak whose cell is >= c
+    alignas(8) uint8_t cell[PA_NCELL];  // cell[c] = index of the first peak whose cell is >= c
 };
 
 struct PsmInfo {
@@ -177,6 +177,15 @@ struct PsmInfo {
     const uint8_t* cell;          // -> smem cell index, or nullptr (binary search over global peaks)
     float cell_base, cell_inv;    // cell(x) = clamp(floor((x - base) * inv), 0, PA_NCELL-1)
 };
+
+// cell width = power of two such that [first peak, last peak] spans fewer than PA_NCELL cells
+__device__ __forceinline__ float pa_cell_inv(float first, float last) {
+    const float range = __fsub_rn(last, first);
+    int e = 0;
+    if (range > 0.f) e = ilogbf(__fmul_rn(range, 1.0f / PA_NCELL)) + 1;
+    e = e < -20 ? -20 : (e > 60 ? 60 : e);
+    return ldexpf(1.0f, -e);
+}
 
 __device__ __forceinline__ int pa_cell(float x, float base, float inv) {
     float c = floorf(__fmul_rn(__fsub_rn(x, base), inv));
@@ -197,6 +206,8 @@ struct PaBatchDev {               // device views of one chunk
     const float* rmz;             // K1 output, indexed with spec_off
     const uint8_t* rrank;
     const int32_t* rcount;
+    const uint8_t* ctab;          // per spectrum PA_NCELL bytes: first retained peak at or after each m/z cell
+    const float2* chead;          // per spectrum {cell base, 1/cell width}; width 0 = no table (binary search)
     int64_t spec_base;            // spec_off values are relative to this peak index
     int64_t n_spec;
 };
@@ -266,29 +277,18 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
         int64_t off = b.spec_off[sp] - b.spec_base;
         int R = b.rcount[sp];
         info.R = R;
-        if (R <= PA_RCAP) {
+        const float2 head = b.chead[sp];
+        if (R <= PA_RCAP && head.y != 0.f) {
             for (int i = lane; i < R; i += 32) { sm->pm[i] = b.rmz[off + i]; sm->pr[i] = b.rrank[off + i]; }
+            // the m/z cell index K1 built for this spectrum (pa_cell is monotone in x, so every
+            // peak before cell[pa_cell(lo)] is <= lo)
+            const unsigned long long* src = (const unsigned long long*)(b.ctab + (size_t)sp * PA_NCELL);
+            ((unsigned long long*)sm->cell)[lane] = src[lane];
             info.pm = sm->pm;
             info.pr = sm->pr;
             info.cell = sm->cell;
-            __syncwarp();
-            // peak index: cell width = power of two so that the peak range spans < PA_NCELL cells.
-            // pa_cell is monotone in x, so every peak before cell[pa_cell(lo)] is <= lo.
-            const float base = R > 0 ? sm->pm[0] : 0.f;
-            const float range = R > 0 ? __fsub_rn(sm->pm[R - 1], base) : 0.f;
-            int e = 0;
-            if (range > 0.f) e = ilogbf(__fmul_rn(range, 1.0f / PA_NCELL)) + 1;
-            e = e < -20 ? -20 : (e > 60 ? 60 : e);
-            const float inv = ldexpf(1.0f, -e);
-            info.cell_base = base;
-            info.cell_inv = inv;
-            for (int j = lane; j < R; j += 32) {
-                const int cj = pa_cell(sm->pm[j], base, inv);
-                const int cp = j > 0 ? pa_cell(sm->pm[j - 1], base, inv) : -1;
-                for (int c = cp + 1; c <= cj; c++) sm->cell[c] = (uint8_t)j;
-                if (j == R - 1) for (int c = cj + 1; c < PA_NCELL; c++) sm->cell[c] = (uint8_t)R;
-            }
-            if (R == 0) for (int c = lane; c < PA_NCELL; c += 32) sm->cell[c] = 0;
+            info.cell_base = head.x;
+            info.cell_inv = head.y;
         } else {
             info.pm = b.rmz + off;
             info.pr = b.rrank + off;

@@ -69,6 +69,8 @@ struct PaBinArgs {
     float* rmz;
     uint8_t* rrank;
     int32_t* rcount;
+    uint8_t* ctab;           // per spectrum PA_NCELL bytes (m/z cell index of the retained peaks)
+    float2* chead;           // per spectrum {cell base, 1 / cell width}
     int32_t* g_bin;          // scratch, one per peak
     uint8_t* g_tmp;          // scratch, one per peak
     float bin_size;
@@ -78,8 +80,9 @@ struct PaBinArgs {
 
 #define PA_NBIN_SMEM 128     // bins whose [start,end) ranges are tabulated in shared memory
 
-// shared memory per warp slot: mz f64[cap] | key u64[cap] | bin i32[cap] | bstart u16[128] | bend u16[128]
-#define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 20 + PA_NBIN_SMEM * 4)
+// shared memory per warp slot: mz f64[cap] (later {float mz, int bin}) | key u64[cap] |
+// bstart u16[128] | bend u16[128] | cell u8[256]
+#define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 16 + PA_NBIN_SMEM * 4 + PA_NCELL)
 
 __device__ __forceinline__ void pa_cp_async8(void* smem_dst, const void* gsrc) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -92,10 +95,12 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
     const int cap = a.cap;
     unsigned char* slot = smem_raw + (size_t)wib * PA_BIN_SLOT_BYTES(cap);
     double* s_mz = (double*)slot;
+    float2* s_mb = (float2*)slot;                 // after binning: {float mz, bin as int bits}, in place
+    float* s_out = (float*)slot;                  // retained (float)mz, compacted in place
     uint64_t* s_key = (uint64_t*)(slot + (size_t)cap * 8);
-    int32_t* s_bin = (int32_t*)(slot + (size_t)cap * 16);
-    uint16_t* s_bstart = (uint16_t*)(slot + (size_t)cap * 20);
+    uint16_t* s_bstart = (uint16_t*)(slot + (size_t)cap * 16);
     uint16_t* s_bend = s_bstart + PA_NBIN_SMEM;
+    uint8_t* s_cell = (uint8_t*)(s_bend + PA_NBIN_SMEM);
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const int n_top = a.n_top;
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
     for (int64_t s = gw; s < a.n_spec; s += nw) {
         const int64_t off = a.spec_off[s] - a.peak_base;
         const int P = (int)(a.spec_off[s + 1] - a.spec_off[s]);
-        if (P <= 0) { if (lane == 0) a.rcount[s] = 0; continue; }
+        if (P <= 0) { if (lane == 0) { a.rcount[s] = 0; a.chead[s] = make_float2(0.f, 0.f); } continue; }
         const bool fits = P <= cap;
         double mn = INF, mx = -INF;
         bool sorted = true;
@@ -160,11 +165,12 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 const int i = base + lane;
                 int bq = -1;
                 if (i < P) {
-                    double q = floor(__ddiv_rn(__dsub_rn(s_mz[i], dmin), dbs));
+                    const double m = s_mz[i];
+                    double q = floor(__ddiv_rn(__dsub_rn(m, dmin), dbs));
                     long long b64 = (long long)q;
                     if (b64 > n_bins - 1) b64 = n_bins - 1;
                     bq = (int)b64;
-                    s_bin[i] = bq;
+                    s_mb[i] = make_float2(__double2float_rn(m), __int_as_float(bq));   // own slot, in place
                     s_key[i] = pa_inten_key(__longlong_as_double((long long)s_key[i]));
                 }
                 int bprev = __shfl_up_sync(PA_FULL, bq, 1);
@@ -180,40 +186,56 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             for (int base = 0; base < P; base += 32) {
                 const int i = base + lane;
                 int cnt = n_top;
+                float mzf = 0.f;
                 if (i < P) {
-                    const int bq = s_bin[i];
+                    const float2 mb = s_mb[i];
+                    mzf = mb.x;
+                    const int bq = __float_as_int(mb.y);
                     const uint64_t ki = s_key[i];
                     cnt = 0;
                     if (tab) {
+                        // rank = peaks of the same bin that beat this one; an equal intensity wins
+                        // only from an earlier index: (kj + [j < i]) > ki covers both sides of i
                         const int b0 = s_bstart[bq], b1 = s_bend[bq];
-                        // rank = peaks of the same bin that beat this one (earlier index wins ties)
                         int j = b0;
-                        for (; j + 4 <= i && cnt < n_top; j += 4) {
+                        for (; j + 4 <= b1; j += 4) {
                             const uint64_t k0 = s_key[j], k1 = s_key[j + 1], k2 = s_key[j + 2], k3 = s_key[j + 3];
-                            cnt += (k0 >= ki) + (k1 >= ki) + (k2 >= ki) + (k3 >= ki);
+                            cnt += ((k0 + (uint64_t)(j < i)) > ki) + ((k1 + (uint64_t)(j + 1 < i)) > ki) +
+                                   ((k2 + (uint64_t)(j + 2 < i)) > ki) + ((k3 + (uint64_t)(j + 3 < i)) > ki);
                         }
-                        for (; j < i; j++) cnt += (s_key[j] >= ki);
-                        j = i + 1;
-                        for (; j + 4 <= b1 && cnt < n_top; j += 4) {
-                            const uint64_t k0 = s_key[j], k1 = s_key[j + 1], k2 = s_key[j + 2], k3 = s_key[j + 3];
-                            cnt += (k0 > ki) + (k1 > ki) + (k2 > ki) + (k3 > ki);
-                        }
-                        for (; j < b1; j++) cnt += (s_key[j] > ki);
+                        for (; j < b1; j++) cnt += ((s_key[j] + (uint64_t)(j < i)) > ki);
                     } else {
-                        for (int j = i - 1; j >= 0 && cnt < n_top && s_bin[j] == bq; j--) cnt += (s_key[j] >= ki);
-                        for (int j = i + 1; j < P && cnt < n_top && s_bin[j] == bq; j++) cnt += (s_key[j] > ki);
+                        for (int j = i - 1; j >= 0 && cnt < n_top && __float_as_int(s_mb[j].y) == bq; j--) cnt += (s_key[j] >= ki);
+                        for (int j = i + 1; j < P && cnt < n_top && __float_as_int(s_mb[j].y) == bq; j++) cnt += (s_key[j] > ki);
                     }
                 }
                 const bool keep = cnt < n_top;
-                unsigned bal = __ballot_sync(PA_FULL, keep);
+                unsigned bal = __ballot_sync(PA_FULL, keep);   // every lane has read its own s_mb slot by now
                 if (keep) {
                     int pos = out + __popc(bal & ((1u << lane) - 1u));
-                    a.rmz[off + pos] = __double2float_rn(s_mz[i]);
+                    a.rmz[off + pos] = mzf;
                     a.rrank[off + pos] = (uint8_t)cnt;
+                    if (tab) s_out[pos] = mzf;      // pos <= i: only slots this or earlier chunks own
                 }
                 out += __popc(bal);
+                __syncwarp();
             }
             if (lane == 0) a.rcount[s] = out;
+            // m/z cell index over the retained peaks (consumers: pa_match_rank)
+            if (tab && out <= PA_RCAP && out > 0) {
+                __syncwarp();
+                const float cbase = s_out[0];
+                const float cinv = pa_cell_inv(cbase, s_out[out - 1]);
+                for (int j = lane; j < out; j += 32) {
+                    const int cj = pa_cell(s_out[j], cbase, cinv);
+                    const int cp = j > 0 ? pa_cell(s_out[j - 1], cbase, cinv) : -1;
+                    for (int c = cp + 1; c <= cj; c++) s_cell[c] = (uint8_t)j;
+                    if (j == out - 1) for (int c = cj + 1; c < PA_NCELL; c++) s_cell[c] = (uint8_t)out;
+                }
+                __syncwarp();
+                ((unsigned long long*)(a.ctab + (size_t)s * PA_NCELL))[lane] = ((const unsigned long long*)s_cell)[lane];
+                if (lane == 0) a.chead[s] = make_float2(cbase, cinv);
+            } else if (lane == 0) a.chead[s] = make_float2(0.f, 0.f);
         } else {
             // general path through global scratch
             for (int i = lane; i < P; i += 32) {
@@ -252,7 +274,7 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 }
                 total += __popc(__ballot_sync(PA_FULL, keep));
             }
-            if (lane == 0) a.rcount[s] = total;
+            if (lane == 0) { a.rcount[s] = total; a.chead[s] = make_float2(0.f, 0.f); }
         }
         __syncwarp();
     }
@@ -620,6 +642,43 @@ __device__ void pa_gcc_sort(unsigned long long* a, long n) {
     else srt_insertion(a, 0, n);
 }
 
+// Only the element std::sort would leave at index 0 is needed on the device (the full listing
+// order is produced on the host by pa_fetch_pep_scores).  Introsort never moves an element from
+// the right part of a partition into the left part afterwards, and the closing insertion sort moves
+// an element left only past strictly smaller scores, so position 0 is decided by the chain of
+// LEFTMOST partitions alone: replay those partitions (O(n) instead of O(n log n)), then take the
+// first maximal element of the final left segment (the insertion sort is stable there).
+__device__ uint32_t pa_gcc_sort_front(unsigned long long* a, long n) {
+    if (n < 1) return 0xffffffffu;
+    long lg = 0;
+    for (long t = n; t > 1; t >>= 1) lg++;
+    long last = n, depth = 2 * lg;
+    const long first = 0;
+    while (last - first > 16) {
+        if (depth == 0) { srt_heap_sort(a, last); return (uint32_t)(a[0] & 0xffffffffull); }
+        --depth;
+        long mid = first + (last - first) / 2;
+        long x = first + 1, y = mid, z = last - 1, pick;
+        if (SRT_CMP(a[x], a[y])) { if (SRT_CMP(a[y], a[z])) pick = y; else if (SRT_CMP(a[x], a[z])) pick = z; else pick = x; }
+        else if (SRT_CMP(a[x], a[z])) pick = x; else if (SRT_CMP(a[y], a[z])) pick = z; else pick = y;
+        { unsigned long long t = a[first]; a[first] = a[pick]; a[pick] = t; }
+        long f = first + 1, l = last;
+        const unsigned long long pv = a[first];
+        for (;;) {
+            while (SRT_CMP(a[f], pv)) f++;
+            --l;
+            while (SRT_CMP(pv, a[l])) l--;
+            if (!(f < l)) break;
+            { unsigned long long t = a[f]; a[f] = a[l]; a[l] = t; }
+            f++;
+        }
+        last = f;
+    }
+    long bi = 0;
+    for (long i = 1; i < last; i++) if (SRT_CMP(a[i], a[bi])) bi = i;
+    return (uint32_t)(a[bi] & 0xffffffffull);
+}
+
 // --- site-determining ions of isoforms A (slot 0) and B (slot 1) for one ion type ------------
 // Returns via hits/trials accumulators (lane-uniform).  `la`,`lb`: list pointers (smem or global).
 __device__ __forceinline__ void pa_sdi_type(const PaCfg& cfg, SelSmem* sm, const PsmInfo& info, char type,
@@ -844,9 +903,7 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                     arr[q] = ((unsigned long long)(uint32_t)__float_as_int(a.iso.w[ib + id]) << 32) | id;
                 }
                 __syncwarp();
-                if (lane == 0) pa_gcc_sort(arr, (long)I);
-                __syncwarp();
-                best = (uint32_t)(arr[0] & 0xffffffffull);
+                if (lane == 0) best = pa_gcc_sort_front(arr, (long)I);
                 best = __shfl_sync(PA_FULL, best, 0);
                 __syncwarp();
             }
@@ -1037,12 +1094,20 @@ __device__ __forceinline__ float asc_pop(const PaCfg& cfg, const AscPep& q, uint
     return x;
 }
 
-__device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int R, float f, float err, int err_gt_half) {
+__device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int R, const uint8_t* ctab, float cbase,
+                                         float cinv, float f, float err, int err_gt_half) {
     const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
-    int a = 0, n = R;
-    while (n > 0) {
-        int h = n >> 1;
-        if (!(__ldg(pm + a + h) > lo)) { a += h + 1; n -= h + 1; } else n = h;
+    int a;
+    if (cinv != 0.f) {
+        a = __ldg(ctab + pa_cell(lo, cbase, cinv));
+        while (a < R && !(__ldg(pm + a) > lo)) a++;
+    } else {
+        a = 0;
+        int n = R;
+        while (n > 0) {
+            int h = n >> 1;
+            if (!(__ldg(pm + a + h) > lo)) { a += h + 1; n -= h + 1; } else n = h;
+        }
     }
     int best = 255;
     for (; a < R; a++) {
@@ -1073,6 +1138,8 @@ __global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscAr
     const float* pm = b.rmz + off;
     const uint8_t* pr = b.rrank + off;
     const int R = b.rcount[sp];
+    const uint8_t* ctab = b.ctab + (size_t)sp * PA_NCELL;
+    const float2 chead = b.chead[sp];
 
     const uint32_t best = a.best_idx[p];
     const uint64_t best_bits = pa_unrank(cfg.binom, S, k, best);
@@ -1136,11 +1203,11 @@ __global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscAr
                     if (!hx && A.left > 0) { x = asc_pop(cfg, q, alo, ahi, fwd, a1, a2, A, mono); hx = true; }
                     if (!hy && B.left > 0) { y = asc_pop(cfg, q, blo, bhi, fwd, a1, a2, B, mono); hy = true; }
                     if (!hx && !hy) break;
-                    if (!hy) { trialsA++; hitsA += asc_match(pm, pr, R, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
-                    else if (!hx) { trialsB++; hitsB += asc_match(pm, pr, R, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
+                    if (!hy) { trialsA++; hitsA += asc_match(pm, pr, R, ctab, chead.x, chead.y, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
+                    else if (!hx) { trialsB++; hitsB += asc_match(pm, pr, R, ctab, chead.x, chead.y, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
                     else if (fabsf(__fsub_rn(x, y)) < cfg.err) { hx = false; hy = false; }
-                    else if (x < y) { trialsA++; hitsA += asc_match(pm, pr, R, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
-                    else { trialsB++; hitsB += asc_match(pm, pr, R, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
+                    else if (x < y) { trialsA++; hitsA += asc_match(pm, pr, R, ctab, chead.x, chead.y, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
+                    else { trialsB++; hitsB += asc_match(pm, pr, R, ctab, chead.x, chead.y, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
                 }
                 if (!mono) generic = true;
             }
