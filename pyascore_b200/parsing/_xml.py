@@ -190,7 +190,10 @@ def iter_pepxml(path, score_string=None):
             for h in _children(sr, "search_hit"):
                 pep = h.get("peptide", "")
                 pos, mass = [], []
-                mi = _child(h, "modification_info")
+                # a hit may carry several <modification_info> blocks (Crux writes one per mod kind);
+                # pyteomics keeps the last one, which test/test_id_parsers.py:192-193 pins
+                mis = _children(h, "modification_info")
+                mi = mis[-1] if mis else None
                 if mi is not None:
                     # pyteomics folds the terminal attributes into the modification list
                     if mi.get("mod_nterm_mass") is not None:
