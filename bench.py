@@ -278,6 +278,18 @@ def main():
             ms += ctr["ms_total"]
         return ms, ctr
 
+    def h2d_peak_gbs(nbytes=1 << 30, reps=4):
+        """plain pinned-host -> device copy rate of this box (what bounds the e2e leg)"""
+        src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        best = 0.0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); dst.copy_(src, non_blocking=True); e1.record(); torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        return best
+
+    pcie_gbs = h2d_peak_gbs() if not args.no_e2e else None
     sampler = ClockSampler(local)
     # ---- value: inputs resident in HBM ----
     run_steps(dev, out_dev, args.warmup)
@@ -338,7 +350,10 @@ def main():
             "config": cfg, "clocks": clocks,
             "e2e": {"value": total_psm / (ms_e2e_max * 1e-3), "unit": "PSM/s",
                     "h2d_bytes_per_step": int(ctr_e2e["bytes_h2d"]), "d2h_bytes_per_step": int(ctr_e2e["bytes_d2h"]),
-                    "ms_per_step": ms_e2e_max / args.steps, "wall_ms_per_step": wall_e2e_ms / args.steps},
+                    "ms_per_step": ms_e2e_max / args.steps, "wall_ms_per_step": wall_e2e_ms / args.steps,
+                    "h2d_achieved_gbs": ctr_e2e["bytes_h2d"] / (ms_e2e_max / args.steps * 1e-3) / 1e9,
+                    "h2d_copy_peak_gbs": pcie_gbs,
+                    "note": "bound by the host->device link: h2d_achieved_gbs vs a plain pinned 1 GiB copy on this box"},
             "gpu_launches": int(ctr_dev["kernel_launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -135,6 +135,41 @@ int pa_site_positions(const pa_scorer* s, const uint8_t* pep, int32_t len, int32
 int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_off, const double* mz,
                    const double* inten, float* out_mz, uint8_t* out_rank, int32_t* out_count);
 
+/* BinnedSpectra probe with the cursor data PyBinnedSpectra exposes (Spectra.pyx:74-125): for every
+ * retained peak also its index inside the input spectrum and its bin; per spectrum
+ * out_bounds[3*s+0..2] = {min_mz, max_mz, n_bins} (cpp/Spectra.cpp:46-52).  Extra outputs may be NULL. */
+int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* spec_off, const double* mz,
+                      const double* inten, float* out_mz, uint8_t* out_rank, int32_t* out_count,
+                      int32_t* out_index, int32_t* out_bin, float* out_bounds);
+
+/* Stage probe behind PyFragmentGraph (ModifiedPeptide.pyx:160-329 -> cpp/ModifiedPeptide.cpp:379-408,
+ * :570-591): for ONE positional isoform `sig` (bit j = site j, N->C) of `pep`, ion type `fragment_type`
+ * and charge `charge` (0 = neutral), the m/z of every neutral-loss variant at every residue step of
+ * the traversal (N->C for b/c, C->N for y/z/Z; the last residue included).
+ * out_mz[step*16 + v], v < out_nvar[step]; both arrays hold `len` steps. */
+int pa_fragment_table(pa_scorer* s, const uint8_t* pep, int32_t len, const uint32_t* aux_pos,
+                      const float* aux_mass, int32_t n_aux, uint64_t sig, char fragment_type, int32_t charge,
+                      float* out_mz, int32_t* out_nvar);
+
+/* Replaces PyModifiedPeptide.get_site_determining_ions (ModifiedPeptide.pyx:117-157 ->
+ * cpp/ModifiedPeptide.cpp:259-320): ions of isoform a not matched (within mz_error) in isoform b and
+ * vice versa, ascending, charges 1..max_charge.  Writes min(count, cap) values; counts in n_a/n_b. */
+int pa_site_determining_ions(pa_scorer* s, const uint8_t* pep, int32_t len, const uint32_t* aux_pos,
+                             const float* aux_mass, int32_t n_aux, uint64_t sig_a, uint64_t sig_b,
+                             char fragment_type, int32_t max_charge, float* out_a, int32_t* n_a,
+                             float* out_b, int32_t* n_b, int32_t cap);
+
+/* Replaces PyLogMath / PyBinomialDist (Util.pyx:6-98 -> cpp/Util.cpp:16-83), n values at once.
+ * op 0: log_sum(x[i], y[i]);  1: log_bin_coef(k[i], tr[i]);  2: log_pmf;  3: log_pvalue;
+ * 4: log10_pvalue of Binomial(tr[i], prob) at k[i] successes.  Unused inputs may be NULL. */
+int pa_log_math(pa_scorer* s, int32_t op, int32_t n, const float* x, const float* y, const int32_t* k,
+                const int32_t* tr, float prob, float* out);
+
+/* Replaces PyPowerSetSum (Util.pyx:100-134 -> cpp/Util.cpp:89-160): sorted, de-duplicated float32
+ * sums of the subsets of `target` with at most max_depth elements (0 first).  Host arithmetic -- it is
+ * the routine that also builds the neutral-loss variant table of the kernels.  Returns the count. */
+int64_t pa_power_set_sums(const float* target, int32_t n, int32_t max_depth, float* out, int64_t cap);
+
 /* Stage probe: the score table |-10 log10 P(X >= k)| for depth d (0-based), n trials, k hits
  * (cpp/Util.cpp:47-83 + cpp/Ascore.cpp:127-133).  out[(n*(n+1)/2 + k)*PA_N_TOP + d], n <= n_max. */
 int pa_tail_table(pa_scorer* s, int32_t n_max, float* out);

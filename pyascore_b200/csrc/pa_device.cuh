@@ -164,16 +164,16 @@ struct PsmSmem {
     float res[PA_LMAX][2];        // residue mass: [i][0] plain, [i][1] with the variable mod
     uint8_t nlidx[PA_LMAX][2];    // neutral-loss index per state (0 = none)
     uint8_t site_pos[64];         // residue index of site j
-    float pm[PA_RCAP + 1];        // retained peaks, (float)mz ascending
-    uint8_t pr[PA_RCAP + 1];      // their ranks
+    float2 pk[PA_RCAP + 1];       // retained peaks {(float)mz ascending, rank as int bits}; pk[R] = {+inf, 255}
     alignas(8) uint8_t cell[PA_NCELL];  // cell[c] = index of the first peak whose cell is >= c
 };
 
 struct PsmInfo {
     int L, k, Z, S, R;
     int status;
-    const float* pm;              // -> smem or global
+    const float* pm;              // global peaks (used when they are not staged: cell == nullptr)
     const uint8_t* pr;
+    const float2* pk;             // staged peaks in shared memory (cell != nullptr)
     const uint8_t* cell;          // -> smem cell index, or nullptr (binary search over global peaks)
     float cell_base, cell_inv;    // cell(x) = clamp(floor((x - base) * inv), 0, PA_NCELL-1)
 };
@@ -279,19 +279,23 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
         info.R = R;
         const float2 head = b.chead[sp];
         if (R <= PA_RCAP && head.y != 0.f) {
-            for (int i = lane; i < R; i += 32) { sm->pm[i] = b.rmz[off + i]; sm->pr[i] = b.rrank[off + i]; }
+            for (int i = lane; i <= R; i += 32)
+                sm->pk[i] = (i < R) ? make_float2(b.rmz[off + i], __int_as_float((int)b.rrank[off + i]))
+                                    : make_float2(__int_as_float(0x7f800000), __int_as_float(255));
             // the m/z cell index K1 built for this spectrum (pa_cell is monotone in x, so every
             // peak before cell[pa_cell(lo)] is <= lo)
             const unsigned long long* src = (const unsigned long long*)(b.ctab + (size_t)sp * PA_NCELL);
             ((unsigned long long*)sm->cell)[lane] = src[lane];
-            info.pm = sm->pm;
-            info.pr = sm->pr;
+            info.pm = b.rmz + off;
+            info.pr = b.rrank + off;
+            info.pk = sm->pk;
             info.cell = sm->cell;
             info.cell_base = head.x;
             info.cell_inv = head.y;
         } else {
             info.pm = b.rmz + off;
             info.pr = b.rrank + off;
+            info.pk = nullptr;
             info.cell = nullptr;
             info.cell_base = 0.f;
             info.cell_inv = 0.f;
@@ -303,23 +307,31 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
 // rank of the best (most intense) retained peak matching theoretical fragment f, or 255.
 // cpp/ModifiedPeptide.cpp:126-142 seen from the fragment's side (SURVEY.md section 7.3 "Matching").
 __device__ __forceinline__ int pa_match_rank(const PsmInfo& info, float f, float err, int err_gt_half) {
+    const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
+    int best = 255;
+    if (info.cell != nullptr) {
+        // staged peaks: every peak before cell[pa_cell(lo)] is <= lo; peaks <= lo inside the cell
+        // are passed over by the same loop (they are < hi), and the +inf sentinel at pk[R] ends it
+        const float2* pk = info.pk + info.cell[pa_cell(lo, info.cell_base, info.cell_inv)];
+        for (;; pk++) {
+            const float2 e = *pk;
+            if (!(e.x < hi)) break;
+            if (e.x > lo && !(err_gt_half && !((double)f >= (double)e.x - .5))) {
+                const int r = __float_as_int(e.y);
+                best = r < best ? r : best;
+            }
+        }
+        return best;
+    }
     const float* pm = info.pm;
     const uint8_t* pr = info.pr;
     const int R = info.R;
-    const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
-    int a;
-    if (info.cell != nullptr) {
-        a = info.cell[pa_cell(lo, info.cell_base, info.cell_inv)];
-        while (a < R && !(pm[a] > lo)) a++;
-    } else {
-        a = 0;
-        int n = R;                          // first index with pm > lo
-        while (n > 0) {
-            int h = n >> 1;
-            if (!(pm[a + h] > lo)) { a += h + 1; n -= h + 1; } else n = h;
-        }
+    int a = 0;
+    int n = R;                          // first index with pm > lo
+    while (n > 0) {
+        int h = n >> 1;
+        if (!(pm[a + h] > lo)) { a += h + 1; n -= h + 1; } else n = h;
     }
-    int best = 255;
     for (; a < R; a++) {
         float p = pm[a];
         if (!(p < hi)) break;
@@ -339,16 +351,18 @@ __device__ __forceinline__ double pa_type_adjust(double d, char type) {
     return d;
 }
 
+// z * 1.007825 for z < 16, filled by the host in IEEE double (the product the reference forms)
+__constant__ double c_zmass[16];
+
 __device__ __forceinline__ float pa_charge_mz(double d, int z) {
     // (d + z * 1.007825) / z  (cpp/ModifiedPeptide.cpp:585-587).  Dividing by 1, 2 or 4 is exact
     // scaling, so the IEEE division routine is only needed for the other charges.
     if (z > 0) {
-        const double zd = (double)z;
-        const double t = __dadd_rn(d, __dmul_rn(zd, 1.007825));
+        const double t = __dadd_rn(d, z < 16 ? c_zmass[z] : __dmul_rn((double)z, 1.007825));
         if (z == 1) d = t;
         else if (z == 2) d = __dmul_rn(t, 0.5);
         else if (z == 4) d = __dmul_rn(t, 0.25);
-        else d = __ddiv_rn(t, zd);
+        else d = __ddiv_rn(t, (double)z);
     }
     return __double2float_rn(d);
 }

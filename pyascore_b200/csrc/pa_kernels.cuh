@@ -73,6 +73,9 @@ struct PaBinArgs {
     float2* chead;           // per spectrum {cell base, 1 / cell width}
     int32_t* g_bin;          // scratch, one per peak
     uint8_t* g_tmp;          // scratch, one per peak
+    int32_t* rindex;         // probe outputs (null on the scoring path): index of each retained peak in
+    int32_t* rbin;           //   its spectrum, its bin, and per spectrum {min_mz, max_mz, n_bins}
+    float* bounds;
     float bin_size;
     int n_top;
     int cap;                 // peaks per warp slot in shared memory
@@ -110,8 +113,8 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
         const int P = (int)(a.spec_off[s + 1] - a.spec_off[s]);
         if (P <= 0) { if (lane == 0) { a.rcount[s] = 0; a.chead[s] = make_float2(0.f, 0.f); } continue; }
         const bool fits = P <= cap;
-        double mn = INF, mx = -INF;
-        bool sorted = true;
+        double mn, mx;
+        bool sorted = fits;
         if (fits) {
             // stage the whole spectrum with asynchronous 8-byte copies: every load of the warp is
             // in flight at once (the arrays are only 8-byte aligned at a CSR offset)
@@ -122,88 +125,100 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncwarp();
-            for (int i = lane; i < P; i += 32) {
-                const double m = s_mz[i];
-                const double prev = i > 0 ? s_mz[i - 1] : -INF;
-                if (m < prev) sorted = false;
-                mn = m < mn ? m : mn;
-                mx = m > mx ? m : mx;
-            }
-        } else {
-            double carry = -INF;
-            for (int base = 0; base < P; base += 32) {
-                int i = base + lane;
-                double m = 0.;
-                if (i < P) m = a.mz[off + i];
-                double prev = __shfl_up_sync(PA_FULL, m, 1);
-                if (lane == 0) prev = carry;
-                if (i < P) {
-                    if (m < prev) sorted = false;
-                    mn = m < mn ? m : mn;
-                    mx = m > mx ? m : mx;
-                }
-                carry = __shfl_sync(PA_FULL, m, 31);
-            }
+            // optimistic: an m/z-sorted spectrum has its extremes at the ends (verified below)
+            mn = s_mz[0]; mx = s_mz[P - 1];
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            double t = __shfl_xor_sync(PA_FULL, mn, o); mn = t < mn ? t : mn;
-            t = __shfl_xor_sync(PA_FULL, mx, o); mx = t > mx ? t : mx;
-        }
-        sorted = __all_sync(PA_FULL, sorted);
-        // cpp/Spectra.cpp:46-48: the 100 is a literal there, independent of bin_size
-        const float min_mz = __double2float_rn(__dmul_rn(floor(__ddiv_rn(mn, 100.)), 100.));
-        const float max_mz = __double2float_rn(__dmul_rn(ceil(__ddiv_rn(mx, 100.)), 100.));
-        long long n_bins = (long long)ceilf(__fdiv_rn(__fsub_rn(max_mz, min_mz), a.bin_size));
-        if (n_bins < 1) n_bins = 1;     // degenerate spectrum: undefined in the reference
-        const double dmin = (double)min_mz, dbs = (double)a.bin_size;
-
-        if (fits && sorted) {
-            const bool tab = n_bins <= PA_NBIN_SMEM;
-            // bins; a sorted spectrum makes every bin one contiguous run [bstart, bend)
+        float min_mz = 0.f, max_mz = 0.f;
+        long long n_bins = 1;
+        double dmin = 0., dbs = (double)a.bin_size;
+        auto bounds = [&]() {
+            // cpp/Spectra.cpp:46-48: the 100 is a literal there, independent of bin_size
+            min_mz = __double2float_rn(__dmul_rn(floor(__ddiv_rn(mn, 100.)), 100.));
+            max_mz = __double2float_rn(__dmul_rn(ceil(__ddiv_rn(mx, 100.)), 100.));
+            n_bins = (long long)ceilf(__fdiv_rn(__fsub_rn(max_mz, min_mz), a.bin_size));
+            if (n_bins < 1) n_bins = 1;     // degenerate spectrum: undefined in the reference
+            dmin = (double)min_mz;
+        };
+        bool tab = false;
+        if (fits) {
+            bounds();
+            tab = n_bins <= PA_NBIN_SMEM;
+            // bins, float m/z and intensity keys, in place; a sorted spectrum makes every bin one
+            // contiguous run [bstart, bend).  Sortedness is checked on what the fast path relies on:
+            // non-decreasing bins and non-decreasing (float)m/z.
+            const double inv_bs = __ddiv_rn(1.0, dbs);
             int carry_bin = -1;
+            float carry_mz = -INFINITY;
             for (int base = 0; base < P; base += 32) {
                 const int i = base + lane;
-                int bq = -1;
+                int bq = 0x7fffffff;
+                float mzf = INFINITY;
                 if (i < P) {
                     const double m = s_mz[i];
-                    double q = floor(__ddiv_rn(__dsub_rn(m, dmin), dbs));
+                    if (m < mn || m > mx) sorted = false;     // the ends must be the true extremes
+                    const double x = __dsub_rn(m, dmin);
+                    // floor(x / bin_size) as the reference computes it; the reciprocal product decides
+                    // unless it lands within 1e-9 of an integer, where the IEEE quotient is taken
+                    double t = __dmul_rn(x, inv_bs);
+                    double q = floor(t);
+                    const double fr = __dsub_rn(t, q);
+                    if (!(fr > 1e-9 && fr < 1. - 1e-9)) q = floor(__ddiv_rn(x, dbs));
                     long long b64 = (long long)q;
                     if (b64 > n_bins - 1) b64 = n_bins - 1;
+                    if (b64 < 0) b64 = 0;           // only reachable for unsorted input (general path follows)
                     bq = (int)b64;
-                    s_mb[i] = make_float2(__double2float_rn(m), __int_as_float(bq));   // own slot, in place
+                    mzf = __double2float_rn(m);
+                    s_mb[i] = make_float2(mzf, __int_as_float(bq));   // own slot, in place
                     s_key[i] = pa_inten_key(__longlong_as_double((long long)s_key[i]));
                 }
                 int bprev = __shfl_up_sync(PA_FULL, bq, 1);
-                if (lane == 0) bprev = carry_bin;
-                if (tab && i < P) {
-                    if (bq != bprev) { s_bstart[bq] = (uint16_t)i; if (i > 0) s_bend[bprev] = (uint16_t)i; }
-                    if (i == P - 1) s_bend[bq] = (uint16_t)P;
+                float mprev = __shfl_up_sync(PA_FULL, mzf, 1);
+                if (lane == 0) { bprev = carry_bin; mprev = carry_mz; }
+                if (i < P) {
+                    if (bq < bprev || mzf < mprev) sorted = false;
+                    if (tab) {
+                        if (bq != bprev) { s_bstart[bq] = (uint16_t)i; if (i > 0 && bprev >= 0 && bprev < PA_NBIN_SMEM) s_bend[bprev] = (uint16_t)i; }
+                        if (i == P - 1) s_bend[bq] = (uint16_t)P;
+                    }
                 }
                 carry_bin = __shfl_sync(PA_FULL, bq, 31);
+                carry_mz = __shfl_sync(PA_FULL, mzf, 31);
             }
+            sorted = __all_sync(PA_FULL, sorted);
             __syncwarp();
+        }
+
+        if (fits && sorted) {
             int out = 0;
+            const uint2* s_k2 = (const uint2*)s_key;        // .y = high word of the intensity key
             for (int base = 0; base < P; base += 32) {
                 const int i = base + lane;
-                int cnt = n_top;
+                int cnt = n_top, bq = 0;
                 float mzf = 0.f;
                 if (i < P) {
                     const float2 mb = s_mb[i];
                     mzf = mb.x;
-                    const int bq = __float_as_int(mb.y);
+                    bq = __float_as_int(mb.y);
                     const uint64_t ki = s_key[i];
                     cnt = 0;
                     if (tab) {
-                        // rank = peaks of the same bin that beat this one; an equal intensity wins
-                        // only from an earlier index: (kj + [j < i]) > ki covers both sides of i
+                        // rank = peaks of the same bin that beat this one.  The high words of the
+                        // keys decide unless another peak of the bin shares this one's high word;
+                        // then the full keys are compared, an equal intensity winning only from an
+                        // earlier index: (kj + [j < i]) > ki covers both sides of i
                         const int b0 = s_bstart[bq], b1 = s_bend[bq];
-                        int j = b0;
-                        for (; j + 4 <= b1; j += 4) {
-                            const uint64_t k0 = s_key[j], k1 = s_key[j + 1], k2 = s_key[j + 2], k3 = s_key[j + 3];
-                            cnt += ((k0 + (uint64_t)(j < i)) > ki) + ((k1 + (uint64_t)(j + 1 < i)) > ki) +
-                                   ((k2 + (uint64_t)(j + 2 < i)) > ki) + ((k3 + (uint64_t)(j + 3 < i)) > ki);
+                        const uint32_t hi = (uint32_t)(ki >> 32);
+                        int eq = 0;
+#pragma unroll 4
+                        for (int j = b0; j < b1; j++) {
+                            const uint32_t h = s_k2[j].y;
+                            cnt += (h > hi);
+                            eq += (h == hi);
                         }
-                        for (; j < b1; j++) cnt += ((s_key[j] + (uint64_t)(j < i)) > ki);
+                        if (eq > 1) {
+                            cnt = 0;
+                            for (int j = b0; j < b1; j++) cnt += ((s_key[j] + (uint64_t)(j < i)) > ki);
+                        }
                     } else {
                         for (int j = i - 1; j >= 0 && cnt < n_top && __float_as_int(s_mb[j].y) == bq; j--) cnt += (s_key[j] >= ki);
                         for (int j = i + 1; j < P && cnt < n_top && __float_as_int(s_mb[j].y) == bq; j++) cnt += (s_key[j] > ki);
@@ -215,12 +230,16 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                     int pos = out + __popc(bal & ((1u << lane) - 1u));
                     a.rmz[off + pos] = mzf;
                     a.rrank[off + pos] = (uint8_t)cnt;
+                    if (a.rindex) { a.rindex[off + pos] = i; a.rbin[off + pos] = bq; }
                     if (tab) s_out[pos] = mzf;      // pos <= i: only slots this or earlier chunks own
                 }
                 out += __popc(bal);
                 __syncwarp();
             }
-            if (lane == 0) a.rcount[s] = out;
+            if (lane == 0) {
+                a.rcount[s] = out;
+                if (a.bounds) { a.bounds[3 * s] = min_mz; a.bounds[3 * s + 1] = max_mz; a.bounds[3 * s + 2] = (float)n_bins; }
+            }
             // m/z cell index over the retained peaks (consumers: pa_match_rank)
             if (tab && out <= PA_RCAP && out > 0) {
                 __syncwarp();
@@ -237,7 +256,18 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 if (lane == 0) a.chead[s] = make_float2(cbase, cinv);
             } else if (lane == 0) a.chead[s] = make_float2(0.f, 0.f);
         } else {
-            // general path through global scratch
+            // general path through global scratch (unsorted or oversized spectra)
+            mn = INF; mx = -INF;
+            for (int i = lane; i < P; i += 32) {
+                const double m = a.mz[off + i];
+                mn = m < mn ? m : mn;
+                mx = m > mx ? m : mx;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                double t = __shfl_xor_sync(PA_FULL, mn, o); mn = t < mn ? t : mn;
+                t = __shfl_xor_sync(PA_FULL, mx, o); mx = t > mx ? t : mx;
+            }
+            bounds();
             for (int i = lane; i < P; i += 32) {
                 double q = floor(__ddiv_rn(__dsub_rn(a.mz[off + i], dmin), dbs));
                 long long bq = (long long)q;
@@ -271,10 +301,14 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                     }
                     a.rmz[off + pos] = fi;
                     a.rrank[off + pos] = a.g_tmp[off + i];
+                    if (a.rindex) { a.rindex[off + pos] = i; a.rbin[off + pos] = a.g_bin[off + i]; }
                 }
                 total += __popc(__ballot_sync(PA_FULL, keep));
             }
-            if (lane == 0) { a.rcount[s] = total; a.chead[s] = make_float2(0.f, 0.f); }
+            if (lane == 0) {
+                a.rcount[s] = total; a.chead[s] = make_float2(0.f, 0.f);
+                if (a.bounds) { a.bounds[3 * s] = min_mz; a.bounds[3 * s + 1] = max_mz; a.bounds[3 * s + 2] = (float)n_bins; }
+            }
         }
         __syncwarp();
     }
@@ -377,49 +411,68 @@ struct PaCountArgs {
     unsigned long long* n_lookups;   // counter
 };
 
-// Walk the fragments of ion types [t0, t1) of the isoform with residue mask (mlo,mhi); returns
-// packed non-cumulative per-rank counts.
+// Walk ion type `type` of the isoform with residue mask (mlo,mhi): the float32 running sum is
+// carried over every step below s1 (the reference's sequential adds), fragments are emitted and
+// matched for steps [s0, s1) only.  Returns packed non-cumulative per-rank counts; `lut[r]` holds
+// the packed increment of rank r (lut[10] = 0 for "no match").
 template <bool HAS_NL>
 __device__ __forceinline__ void pa_walk_isoform(const PaCfg& cfg, const PsmSmem* sm, const PsmInfo& info,
-                                                uint64_t mlo, uint64_t mhi, int t0, int t1,
-                                                unsigned long long& clo, unsigned long long& chi,
-                                                uint32_t& nfrag) {
+                                                uint64_t mlo, uint64_t mhi, char type, int s0, int s1,
+                                                const ulonglong2* lut, unsigned long long& clo,
+                                                unsigned long long& chi, uint32_t& nfrag) {
     const int L = info.L, Z = info.Z;
     clo = 0; chi = 0; nfrag = 0;
-    // L == 1: the walk starts on the last residue and the reference's end test lets all but
-    // the last neutral-loss variant through (cpp/ModifiedPeptide.cpp:516-524)
-    const int steps = (L == 1) ? 1 : L - 1;
-    for (int t = t0; t < t1; t++) {
-        const char type = cfg.types[t];
-        const bool fwd = (type == 'b' || type == 'c');
-        double a1, a2;
-        pa_type_consts(type, a1, a2);
-        float run = 0.f;
-        int nls = 0;
-        for (int step = 0; step < steps; step++) {
-            const int i = fwd ? step : L - 1 - step;
-            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-            const float r = sm->res[i][st];
-            run = (step == 0) ? r : __fadd_rn(r, run);
-            int nv = 1;
-            if (HAS_NL) {
-                int idx = sm->nlidx[i][st];
-                if (idx) nls = pa_nl_bump(nls, idx);
-                nv = cfg.nl_nvar[nls];
+    const bool fwd = (type == 'b' || type == 'c');
+    double a1, a2;
+    pa_type_consts(type, a1, a2);
+    const double zm1 = c_zmass[1], zm2 = c_zmass[2];
+    float run = 0.f;             // r + 0.f == r: the first step needs no special case
+    int nls = 0;
+    // replay: the lanes of a split walk have different s0, but this loop is cheap; the matching
+    // loop below then runs in lock step over all lanes of the warp
+    for (int step = 0; step < s0; step++) {
+        const int i = fwd ? step : L - 1 - step;
+        const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+        run = __fadd_rn(sm->res[i][st], run);
+        if (HAS_NL) {
+            int idx = sm->nlidx[i][st];
+            if (idx) nls = pa_nl_bump(nls, idx);
+        }
+    }
+    for (int step = s0; step < s1; step++) {
+        const int i = fwd ? step : L - 1 - step;
+        const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+        run = __fadd_rn(sm->res[i][st], run);
+        int nv = 1;
+        if (HAS_NL) {
+            int idx = sm->nlidx[i][st];
+            if (idx) nls = pa_nl_bump(nls, idx);
+            nv = cfg.nl_nvar[nls];
+        }
+        // L == 1: the walk starts on the last residue and the reference's end test lets all but
+        // the last neutral-loss variant through (cpp/ModifiedPeptide.cpp:516-524)
+        if (L == 1) nv -= 1;
+        for (int v = 0; v < nv; v++) {
+            float base = run;
+            if (HAS_NL) base = __fsub_rn(run, __ldg(cfg.nl_sums + nls * 16 + v));
+            const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
+            // charge z: (d + z * 1.007825) / z  (cpp/ModifiedPeptide.cpp:585-587); 1 and 2 are unrolled
+            {
+                const int rk = pa_match_rank(info, __double2float_rn(__dadd_rn(d, zm1)), cfg.err, cfg.err_gt_half);
+                const ulonglong2 inc = lut[rk < 10 ? rk : 10];
+                clo += inc.x; chi += inc.y;
             }
-            if (L == 1) nv -= 1;
-            for (int v = 0; v < nv; v++) {
-                float base = run;
-                if (HAS_NL) base = __fsub_rn(run, __ldg(cfg.nl_sums + nls * 16 + v));
-                const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
-                for (int z = 1; z <= Z; z++) {
-                    const float f = pa_charge_mz(d, z);
-                    const int rk = pa_match_rank(info, f, cfg.err, cfg.err_gt_half);
-                    if (rk < 5) clo += 1ull << (12 * rk);
-                    else if (rk < 10) chi += 1ull << (12 * (rk - 5));
-                }
-                nfrag += Z;
+            if (Z >= 2) {
+                const int rk = pa_match_rank(info, __double2float_rn(__dmul_rn(__dadd_rn(d, zm2), 0.5)), cfg.err, cfg.err_gt_half);
+                const ulonglong2 inc = lut[rk < 10 ? rk : 10];
+                clo += inc.x; chi += inc.y;
             }
+            for (int z = 3; z <= Z; z++) {
+                const int rk = pa_match_rank(info, pa_charge_mz(d, z), cfg.err, cfg.err_gt_half);
+                const ulonglong2 inc = lut[rk < 10 ? rk : 10];
+                clo += inc.x; chi += inc.y;
+            }
+            nfrag += Z;
         }
     }
 }
@@ -459,44 +512,67 @@ __device__ __forceinline__ void pa_sites_to_mask(const PsmSmem* sm, uint64_t bit
     }
 }
 
-// PAIR: exactly two ion types (the default "by"): adjacent lanes take the two types of one isoform
-// and add their counts with one shuffle, so small PSMs keep twice as many lanes busy.
+// Lane mapping inside a unit: isoform x ion type x segment.  PAIR (exactly two ion types, the
+// default "by") gives each type of an isoform its own lane; when the unit has few isoforms each
+// walk is further split into H segments of consecutive steps (a lane replays the cheap running sum
+// up to its segment and matches only its own fragments), so that small PSMs still fill the warp.
+// The lanes of one isoform are contiguous and add their packed counts with xor-shuffles.
 template <bool HAS_NL, bool PAIR>
 __global__ void __launch_bounds__(256) k_count_score(PaCfg cfg, PaBatchDev b, PaCountArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ ulonglong2 s_lut[16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    if (threadIdx.x < 16) {
+        const int r = threadIdx.x;
+        s_lut[r] = make_ulonglong2(r < 5 ? 1ull << (12 * r) : 0ull, (r >= 5 && r < 10) ? 1ull << (12 * (r - 5)) : 0ull);
+    }
+    __syncthreads();
     PsmSmem* sm = (PsmSmem*)smem_raw + wib;
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     int64_t cur = -1;
     PsmInfo info;
     unsigned long long lookups = 0;
+    const int T = PAIR ? 2 : 1;
     for (int64_t u = gw; u < a.n_units; u += nw) {
         const int64_t p = a.unit_psm[u];
         if (p != cur) { pa_setup_psm(cfg, b, p, sm, info, true); cur = p; }
         const int S = a.psm_S[p], k = info.k;
         const int64_t I = a.iso_off[p + 1] - a.iso_off[p];
         const int64_t first = (int64_t)(u - a.unit_off[p]) * PA_UNIT;
-        const int64_t cnt = (I - first < PA_UNIT) ? I - first : PA_UNIT;
-        const int64_t items = PAIR ? 2 * cnt : cnt;
-        for (int64_t q0 = 0; q0 < items; q0 += 32) {
-            const int64_t q = q0 + lane;
+        const int cnt = (int)((I - first < PA_UNIT) ? I - first : PA_UNIT);
+        const int steps = (info.L == 1) ? 1 : info.L - 1;
+        int hs = 0;                                  // log2 of the segments per walk
+        while (hs < 3 && (cnt * T << (hs + 1)) <= 32 && (2 << hs) <= steps) hs++;
+        const int H = 1 << hs, gs = hs + (PAIR ? 1 : 0), G = 1 << gs;      // G lanes per isoform
+        const int items = cnt << gs;
+        for (int q0 = 0; q0 < items; q0 += 32) {
+            const int q = q0 + lane;
             const bool active = q < items;
-            const uint32_t idx = (uint32_t)(first + (PAIR ? (q >> 1) : q));
+            const uint32_t idx = (uint32_t)(first + (q >> gs));
+            const int sub = q & (G - 1), h = sub & (H - 1);
             unsigned long long clo = 0, chi = 0; uint32_t nf = 0;
             if (active) {
                 const uint64_t bits = pa_unrank(cfg.binom, S, k, idx);
                 uint64_t mlo, mhi;
                 pa_sites_to_mask(sm, bits, mlo, mhi);
-                const int t0 = PAIR ? (int)(q & 1) : 0, t1 = PAIR ? t0 + 1 : cfg.n_types;
-                pa_walk_isoform<HAS_NL>(cfg, sm, info, mlo, mhi, t0, t1, clo, chi, nf);
+                const int s0 = (steps * h) >> hs, s1 = (steps * (h + 1)) >> hs;
+                if (PAIR) {
+                    pa_walk_isoform<HAS_NL>(cfg, sm, info, mlo, mhi, cfg.types[sub >> hs], s0, s1, s_lut, clo, chi, nf);
+                } else {
+                    for (int t = 0; t < cfg.n_types; t++) {
+                        unsigned long long xlo, xhi; uint32_t xn;
+                        pa_walk_isoform<HAS_NL>(cfg, sm, info, mlo, mhi, cfg.types[t], s0, s1, s_lut, xlo, xhi, xn);
+                        clo += xlo; chi += xhi; nf += xn;
+                    }
+                }
                 lookups += nf;
             }
-            if (PAIR) {
-                clo += __shfl_xor_sync(PA_FULL, clo, 1);
-                chi += __shfl_xor_sync(PA_FULL, chi, 1);
-                nf += __shfl_xor_sync(PA_FULL, nf, 1);
+            for (int o = 1; o < G; o <<= 1) {
+                clo += __shfl_xor_sync(PA_FULL, clo, o);
+                chi += __shfl_xor_sync(PA_FULL, chi, o);
+                nf += __shfl_xor_sync(PA_FULL, nf, o);
             }
-            if (active && (!PAIR || (lane & 1) == 0)) {
+            if (active && sub == 0) {
                 pa_cumulate(clo, chi);
                 const int64_t g = a.iso_off[p] + idx;
                 a.iso.lo[g] = clo; a.iso.hi[g] = chi; a.iso.nfrag[g] = nf;
@@ -548,6 +624,9 @@ struct PaSelArgs {
     uint32_t* best_idx;          // [n_psm] best isoform (lexicographic rank), 0xffffffff = none
     int32_t* mod_psm;            // [entries] chunk-relative PSM of each mod entry, -1 = no Ascore to compute
     unsigned long long* tie;     // [entries] tied best competitors of each mod entry
+    int32_t* work_list;          // [4][work_cap] entries whose Ascore needs the site-determining-ion comparison,
+    int* work_count;             // [4]              by stream class (k_ascore)
+    int64_t work_cap;
 };
 
 // --- libstdc++ std::sort (introsort + final insertion sort), comparator a.w > b.w ------------
@@ -935,6 +1014,18 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 if (a.alt_sites) a.alt_sites[mo + j] = tie;
                 a.tie[mo + j - a.mod_lo] = tie;
                 a.mod_psm[mo + j - a.mod_lo] = (int32_t)p;
+                if (a.ascores) {
+                    // a single tied competitor within 1e-6 of the best score: Ascore 0 without looking
+                    // at any ion (cpp/Ascore.cpp:161-163); everything else is queued for k_ascore
+                    const float wb = a.iso.w[ib + best];
+                    if ((tie & (tie - 1)) == 0 && (double)fabsf(__fsub_rn(wb, m)) < 1e-6) a.ascores[mo + j] = 0.f;
+                    else {
+                        // queued by stream count so that the lanes of a k_ascore warp run the same code
+                        const int Z = b.max_charge[p];
+                        const int cls = cfg.has_nl ? 3 : (Z == 1 ? 0 : (Z == 2 ? 1 : (Z <= 4 ? 2 : 3)));
+                        a.work_list[(int64_t)cls * a.work_cap + atomicAdd(a.work_count + cls, 1)] = (int32_t)(mo + j - a.mod_lo);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -963,6 +1054,9 @@ struct PaAscArgs {
     const int32_t* psm_S;
     PaIso iso;
     float* ascores;              // absolute-indexed output (may be null)
+    const int32_t* work_list;    // [4][work_cap] entries queued by k_select, by stream class
+    const int* work_count;       // [4]
+    int64_t work_cap;
     int32_t* generic_list;       // entries that need the generic kernel
     int* generic_count;
 };
@@ -972,6 +1066,7 @@ struct AscPep {                  // what a thread needs to know about its peptid
     int L, Z, a0, a1;
     const uint32_t* aux_pos;
     const float* aux_mass;
+    uint64_t aux_lo, aux_hi;     // residues that carry a fixed mod
 };
 
 // residue mass / neutral-loss index of residue i in modification state st
@@ -982,116 +1077,161 @@ __device__ __forceinline__ float asc_res(const PaCfg& cfg, const AscPep& q, int 
     if (st) m = __fadd_rn(m, cfg.mod_mass);
     nlidx = 0;
     if (cfg.has_nl) nlidx = st ? __ldg(cfg.nl_lo_tab + c) : __ldg(cfg.nl_up_tab + c);
-    for (int a = q.a0; a < q.a1; a++) {
-        const uint32_t pos = q.aux_pos[a];
-        const int idx = pos > 0 ? (int)pos - 1 : 0;
-        if (idx == i) {
-            m = __fadd_rn(m, q.aux_mass[a]);
-            if (cfg.has_nl && __ldg(cfg.nl_lo_tab + c)) nlidx = __ldg(cfg.nl_lo_tab + c);
+    if (((i < 64) ? (q.aux_lo >> i) : (q.aux_hi >> (i - 64))) & 1ull) {
+        for (int a = q.a0; a < q.a1; a++) {
+            const uint32_t pos = q.aux_pos[a];
+            const int idx = pos > 0 ? (int)pos - 1 : 0;
+            if (idx == i) {
+                m = __fadd_rn(m, q.aux_mass[a]);
+                if (cfg.has_nl && __ldg(cfg.nl_lo_tab + c)) nlidx = __ldg(cfg.nl_lo_tab + c);
+            }
         }
     }
     return m;
 }
 
-struct AscList {                 // streams of one isoform for one ion type
-    float run[PA_MAXSTREAM];
-    float val[PA_MAXSTREAM];
-    float sigma[PA_MAXSTREAM];
-    short step[PA_MAXSTREAM];
-    short zq[PA_MAXSTREAM];
+// Streams of one isoform for one ion type.  NQ <= 4: everything lives in registers (loops are
+// unrolled and a stream is addressed by compare-and-select); NQ = PA_MAXSTREAM: dynamic indexing.
+template <int NQ>
+struct AscList {
+    float run[NQ];
+    float val[NQ];
+    float sigma[NQ];
+    int step[NQ];
+    int zq[NQ];
     int nq;                      // number of streams
     int left;                    // elements not yet popped
 };
 
 // returns false when the shape is not supported by the streaming formulation
+template <int NQ>
 __device__ __forceinline__ bool asc_init(const PaCfg& cfg, const AscPep& q, uint64_t mlo, uint64_t mhi, bool fwd,
-                                         double a1, double a2, AscList& ls) {
+                                         double a1, double a2, AscList<NQ>& ls) {
     const int L = q.L, Z = q.Z, steps = L - 1;
-    float sig[PA_MAXSTREAM], run_at[PA_MAXSTREAM];
-    short start[PA_MAXSTREAM];
-    int V = 1;
-    if (!cfg.has_nl) {
-        // one stream per charge: no loss (sigma 0), present from the first residue on
-        if (Z > PA_MAXSTREAM) return false;
+    if (NQ <= 4) {
+        // no neutral loss: one stream per charge, present from the first residue on
         const int i = fwd ? 0 : L - 1;
         const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
         int idx;
-        sig[0] = 0.f; start[0] = 0;
-        run_at[0] = asc_res(cfg, q, i, st, idx);
+        const float r0 = asc_res(cfg, q, i, st, idx);
+        const double d = __dsub_rn(__dadd_rn((double)r0, a1), a2);
+        ls.nq = Z; ls.left = Z * steps;
+#pragma unroll
+        for (int z = 0; z < NQ; z++) {
+            ls.run[z] = r0; ls.sigma[z] = 0.f; ls.step[z] = 0; ls.zq[z] = z + 1;
+            ls.val[z] = (z < Z) ? pa_charge_mz(d, z + 1) : __int_as_float(0x7f800000);
+        }
+        return true;
     } else {
-        // pass 1: the final neutral-loss state says which sums will ever exist
-        int nls = 0;
-        for (int step = 0; step < steps; step++) {
+        float sig[PA_MAXSTREAM], run_at[PA_MAXSTREAM];
+        int start[PA_MAXSTREAM];
+        int V = 1;
+        if (!cfg.has_nl) {
+            if (Z > PA_MAXSTREAM) return false;
+            const int i = fwd ? 0 : L - 1;
+            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+            int idx;
+            sig[0] = 0.f; start[0] = 0;
+            run_at[0] = asc_res(cfg, q, i, st, idx);
+        } else {
+            // pass 1: the final neutral-loss state says which sums will ever exist
+            int nls = 0;
+            for (int step = 0; step < steps; step++) {
+                const int i = fwd ? step : L - 1 - step;
+                const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+                int idx;
+                (void)asc_res(cfg, q, i, st, idx);
+                if (idx) nls = pa_nl_bump(nls, idx);
+            }
+            V = cfg.nl_nvar[nls];
+            if (V * Z > PA_MAXSTREAM) return false;
+            for (int v = 0; v < V; v++) { sig[v] = __ldg(cfg.nl_sums + nls * 16 + v); start[v] = -1; run_at[v] = 0.f; }
+            // pass 2: the step at which each sum first becomes available (the stack only grows, so
+            // it stays available afterwards) and the running sum there
+            int started = 0;
+            float run = 0.f;
+            nls = 0;
+            for (int step = 0; step < steps && started < V; step++) {
+                const int i = fwd ? step : L - 1 - step;
+                const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
+                int idx;
+                const float r = asc_res(cfg, q, i, st, idx);
+                run = (step == 0) ? r : __fadd_rn(r, run);
+                const int before = nls;
+                if (idx) nls = pa_nl_bump(nls, idx);
+                if (step == 0 || nls != before) {
+                    const int nv = cfg.nl_nvar[nls];
+                    for (int v = 0; v < V; v++) {
+                        if (start[v] >= 0) continue;
+                        bool in = false;
+                        for (int u = 0; u < nv; u++) in |= (__ldg(cfg.nl_sums + nls * 16 + u) == sig[v]);
+                        if (in) { start[v] = step; run_at[v] = run; started++; }
+                    }
+                }
+            }
+        }
+        ls.nq = 0; ls.left = 0;
+        for (int v = 0; v < V; v++) {
+            if (cfg.has_nl && start[v] < 0) continue;     // cannot happen: every final sum appears somewhere
+            for (int z = 1; z <= Z; z++) {
+                const int qi = ls.nq++;
+                ls.run[qi] = run_at[v]; ls.sigma[qi] = sig[v]; ls.step[qi] = start[v]; ls.zq[qi] = z;
+                const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run_at[v], sig[v]), a1), a2);
+                ls.val[qi] = pa_charge_mz(d, z);
+                ls.left += steps - start[v];
+            }
+        }
+        return true;
+    }
+}
+
+// pop the smallest pending fragment of the list; `mono` is cleared if a stream ever decreases
+template <int NQ>
+__device__ __forceinline__ float asc_pop(const PaCfg& cfg, const AscPep& q, uint64_t mlo, uint64_t mhi, bool fwd,
+                                         double a1, double a2, AscList<NQ>& ls, bool& mono) {
+    const int L = q.L, steps = L - 1;
+    const float PINF = __int_as_float(0x7f800000);
+    int bq = 0;
+    float x = ls.val[0];
+    if (NQ <= 4) {
+        float runb = ls.run[0];
+        int stepb = ls.step[0];
+#pragma unroll
+        for (int i = 1; i < NQ; i++) { const float v = ls.val[i]; if (v < x) { x = v; bq = i; runb = ls.run[i]; stepb = ls.step[i]; } }
+        const int step = stepb + 1;
+        ls.left--;
+        float nv = PINF, run = runb;
+        if (step < steps) {
             const int i = fwd ? step : L - 1 - step;
             const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
             int idx;
-            (void)asc_res(cfg, q, i, st, idx);
-            if (idx) nls = pa_nl_bump(nls, idx);
+            run = __fadd_rn(asc_res(cfg, q, i, st, idx), runb);
+            const double d = __dsub_rn(__dadd_rn((double)run, a1), a2);     // sigma == 0: run - 0 == run
+            nv = pa_charge_mz(d, bq + 1);
+            if (nv < x) mono = false;
         }
-        V = cfg.nl_nvar[nls];
-        if (V * Z > PA_MAXSTREAM) return false;
-        for (int v = 0; v < V; v++) { sig[v] = __ldg(cfg.nl_sums + nls * 16 + v); start[v] = -1; run_at[v] = 0.f; }
-        // pass 2: the step at which each sum first becomes available (the stack only grows, so
-        // it stays available afterwards) and the running sum there
-        int started = 0;
-        float run = 0.f;
-        nls = 0;
-        for (int step = 0; step < steps && started < V; step++) {
+#pragma unroll
+        for (int i = 0; i < NQ; i++) if (i == bq) { ls.run[i] = run; ls.step[i] = step; ls.val[i] = nv; }
+        return x;
+    } else {
+        for (int i = 1; i < ls.nq; i++) { const float v = ls.val[i]; if (v < x) { x = v; bq = i; } }
+        const int step = ls.step[bq] + 1;
+        ls.step[bq] = step;
+        ls.left--;
+        if (step < steps) {
             const int i = fwd ? step : L - 1 - step;
             const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
             int idx;
             const float r = asc_res(cfg, q, i, st, idx);
-            run = (step == 0) ? r : __fadd_rn(r, run);
-            const int before = nls;
-            if (idx) nls = pa_nl_bump(nls, idx);
-            if (step == 0 || nls != before) {
-                const int nv = cfg.nl_nvar[nls];
-                for (int v = 0; v < V; v++) {
-                    if (start[v] >= 0) continue;
-                    bool in = false;
-                    for (int u = 0; u < nv; u++) in |= (__ldg(cfg.nl_sums + nls * 16 + u) == sig[v]);
-                    if (in) { start[v] = (short)step; run_at[v] = run; started++; }
-                }
-            }
-        }
+            const float run = __fadd_rn(r, ls.run[bq]);
+            ls.run[bq] = run;
+            const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run, ls.sigma[bq]), a1), a2);
+            const float nv = pa_charge_mz(d, ls.zq[bq]);
+            if (nv < x) mono = false;
+            ls.val[bq] = nv;
+        } else ls.val[bq] = PINF;
+        return x;
     }
-    ls.nq = 0; ls.left = 0;
-    for (int v = 0; v < V; v++) {
-        if (cfg.has_nl && start[v] < 0) continue;     // cannot happen: every final sum appears somewhere
-        for (int z = 1; z <= Z; z++) {
-            const int qi = ls.nq++;
-            ls.run[qi] = run_at[v]; ls.sigma[qi] = sig[v]; ls.step[qi] = start[v]; ls.zq[qi] = (short)z;
-            const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run_at[v], sig[v]), a1), a2);
-            ls.val[qi] = pa_charge_mz(d, z);
-            ls.left += steps - start[v];
-        }
-    }
-    return true;
-}
-
-// pop the smallest pending fragment of the list; `mono` is cleared if a stream ever decreases
-__device__ __forceinline__ float asc_pop(const PaCfg& cfg, const AscPep& q, uint64_t mlo, uint64_t mhi, bool fwd,
-                                         double a1, double a2, AscList& ls, bool& mono) {
-    int bq = 0;
-    float x = ls.val[0];
-    for (int i = 1; i < ls.nq; i++) { const float v = ls.val[i]; if (v < x) { x = v; bq = i; } }
-    const int L = q.L, steps = L - 1;
-    const int step = ls.step[bq] + 1;
-    ls.step[bq] = (short)step;
-    ls.left--;
-    if (step < steps) {
-        const int i = fwd ? step : L - 1 - step;
-        const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-        int idx;
-        const float r = asc_res(cfg, q, i, st, idx);
-        const float run = __fadd_rn(r, ls.run[bq]);
-        ls.run[bq] = run;
-        const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run, ls.sigma[bq]), a1), a2);
-        const float nv = pa_charge_mz(d, ls.zq[bq]);
-        if (nv < x) mono = false;
-        ls.val[bq] = nv;
-    } else ls.val[bq] = __int_as_float(0x7f800000);
-    return x;
 }
 
 __device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int R, const uint8_t* ctab, float cbase,
@@ -1100,7 +1240,6 @@ __device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int
     int a;
     if (cinv != 0.f) {
         a = __ldg(ctab + pa_cell(lo, cbase, cinv));
-        while (a < R && !(__ldg(pm + a) > lo)) a++;
     } else {
         a = 0;
         int n = R;
@@ -1113,6 +1252,7 @@ __device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int
     for (; a < R; a++) {
         const float p = __ldg(pm + a);
         if (!(p < hi)) break;
+        if (!(p > lo)) continue;
         if (err_gt_half && !((double)f >= (double)p - .5)) continue;
         const int r = __ldg(pr + a);
         best = r < best ? r : best;
@@ -1120,52 +1260,173 @@ __device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int
     return best;
 }
 
-__global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_entries) return;
+struct AscPeaks {
+    const float* pm; const uint8_t* pr; int R; const uint8_t* ctab; float cbase, cinv;
+};
+
+// greedy tolerance merge of cpp/ModifiedPeptide.cpp:288-316 over the streams of the best isoform
+// (mask a) and one competitor (mask b) for one ion type; false = needs the generic kernel.
+// The loop is written as a small state machine -- at most one pop per trip, taken from whichever
+// list lacks a head, then one decision when both heads are settled -- so that the lanes of a
+// warp, which sit at different points of different merges, still execute the same instructions.
+template <int NQ>
+__device__ __forceinline__ bool asc_merge_type(const PaCfg& cfg, const AscPep& q, const AscPeaks& pk, char type,
+                                               uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi, int depth,
+                                               int& hitsA, int& trialsA, int& hitsB, int& trialsB) {
+    const bool fwd = (type == 'b' || type == 'c');
+    double a1, a2;
+    pa_type_consts(type, a1, a2);
+    bool mono = true;
+    float x = 0.f, y = 0.f;
+    bool hx = false, hy = false;         // a popped element is pending
+    if (NQ <= 4) {
+        // no neutral loss: stream z-1 holds charge z; everything in registers
+        const int L = q.L, Z = q.Z, steps = L - 1;
+        const float PINF = __int_as_float(0x7f800000);
+        float runA[NQ], valA[NQ], runB[NQ], valB[NQ];
+        int stepA[NQ], stepB[NQ];
+        {
+            const int i = fwd ? 0 : L - 1;
+            int idx;
+            const float rA = asc_res(cfg, q, i, (int)(((i < 64) ? (alo >> i) : (ahi >> (i - 64))) & 1ull), idx);
+            const float rB = asc_res(cfg, q, i, (int)(((i < 64) ? (blo >> i) : (bhi >> (i - 64))) & 1ull), idx);
+            const double dA = __dsub_rn(__dadd_rn((double)rA, a1), a2), dB = __dsub_rn(__dadd_rn((double)rB, a1), a2);
+#pragma unroll
+            for (int z = 0; z < NQ; z++) {
+                runA[z] = rA; runB[z] = rB; stepA[z] = 0; stepB[z] = 0;
+                valA[z] = (z < Z) ? pa_charge_mz(dA, z + 1) : PINF;
+                valB[z] = (z < Z) ? pa_charge_mz(dB, z + 1) : PINF;
+            }
+        }
+        int leftA = Z * steps, leftB = Z * steps;
+        for (;;) {
+            const bool needA = !hx && leftA > 0, needB = !hy && leftB > 0;
+            if (needA || needB) {
+                const bool w = !needA;                           // pop from B only when A has its head
+                int bq = 0;
+                float xm = w ? valB[0] : valA[0], runb = w ? runB[0] : runA[0];
+                int stepb = w ? stepB[0] : stepA[0];
+#pragma unroll
+                for (int i = 1; i < NQ; i++) {
+                    const float v = w ? valB[i] : valA[i];
+                    if (v < xm) { xm = v; bq = i; runb = w ? runB[i] : runA[i]; stepb = w ? stepB[i] : stepA[i]; }
+                }
+                const int step = stepb + 1;
+                float nv = PINF, run = runb;
+                if (step < steps) {
+                    const int i = fwd ? step : L - 1 - step;
+                    const uint64_t mlo = w ? blo : alo, mhi = w ? bhi : ahi;
+                    int idx;
+                    run = __fadd_rn(asc_res(cfg, q, i, (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull), idx), runb);
+                    nv = pa_charge_mz(__dsub_rn(__dadd_rn((double)run, a1), a2), bq + 1);
+                    if (nv < xm) mono = false;
+                }
+#pragma unroll
+                for (int i = 0; i < NQ; i++) {
+                    if (i == bq) {
+                        if (w) { runB[i] = run; stepB[i] = step; valB[i] = nv; }
+                        else { runA[i] = run; stepA[i] = step; valA[i] = nv; }
+                    }
+                }
+                if (w) { y = xm; hy = true; leftB--; } else { x = xm; hx = true; leftA--; }
+            }
+            if ((hx || leftA == 0) && (hy || leftB == 0)) {
+                if (!hx && !hy) break;
+                int takeA;                       // 1: A survives, 0: B survives, -1: both dropped
+                if (!hy) takeA = 1;
+                else if (!hx) takeA = 0;
+                else if (fabsf(__fsub_rn(x, y)) < cfg.err) takeA = -1;
+                else takeA = x < y;
+                if (takeA < 0) { hx = false; hy = false; }
+                else {
+                    const int hit = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, takeA ? x : y, cfg.err, cfg.err_gt_half) <= depth;
+                    if (takeA) { trialsA++; hitsA += hit; hx = false; }
+                    else { trialsB++; hitsB += hit; hy = false; }
+                }
+            }
+        }
+        return mono;
+    } else {
+        AscList<NQ> A, B;
+        if (!asc_init<NQ>(cfg, q, alo, ahi, fwd, a1, a2, A) || !asc_init<NQ>(cfg, q, blo, bhi, fwd, a1, a2, B)) return false;
+        for (;;) {
+            if (!hx && A.left > 0) { x = asc_pop<NQ>(cfg, q, alo, ahi, fwd, a1, a2, A, mono); hx = true; }
+            if (!hy && B.left > 0) { y = asc_pop<NQ>(cfg, q, blo, bhi, fwd, a1, a2, B, mono); hy = true; }
+            if (!hx && !hy) break;
+            int takeA;
+            if (!hy) takeA = 1;
+            else if (!hx) takeA = 0;
+            else if (fabsf(__fsub_rn(x, y)) < cfg.err) takeA = -1;
+            else takeA = x < y;
+            if (takeA < 0) { hx = false; hy = false; continue; }
+            const int rk = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, takeA ? x : y, cfg.err, cfg.err_gt_half);
+            if (takeA) { trialsA++; hitsA += rk <= depth; hx = false; }
+            else { trialsB++; hitsB += rk <= depth; hy = false; }
+        }
+        return mono;
+    }
+}
+
+// residue index of modifiable site `u` (sites count the modifiable residues N->C)
+__device__ __forceinline__ int asc_site_pos(const PaCfg& cfg, const AscPep& q, int u) {
+    int n = 0;
+    for (int i = 0; i < q.L; i++) {
+        const int c = (int)q.pep[i] - 'A';
+        const bool is = ((cfg.mod_letters >> c) & 1u) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == q.L - 1);
+        if (is) { if (n == u) return i; n++; }
+    }
+    return 0;
+}
+
+template <int NQ>
+__device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b, const PaAscArgs& a, int64_t t) {
     const int32_t p = a.mod_psm[t];
-    if (p < 0) return;
     const int j = (int)(a.mod_lo + t - a.mod_off[p]);
     const int S = a.psm_S[p], k = b.n_mod[p];
     const int64_t ib = a.iso_off[p];
     AscPep q;
     const int po = b.pep_off[p];
     q.pep = b.pep + po; q.L = b.pep_off[p + 1] - po; q.Z = b.max_charge[p];
-    q.a0 = 0; q.a1 = 0; q.aux_pos = b.aux_pos; q.aux_mass = b.aux_mass;
-    if (b.aux_off != nullptr) { q.a0 = b.aux_off[p]; q.a1 = b.aux_off[p + 1]; }
+    q.a0 = 0; q.a1 = 0; q.aux_pos = b.aux_pos; q.aux_mass = b.aux_mass; q.aux_lo = 0; q.aux_hi = 0;
+    if (b.aux_off != nullptr) {
+        q.a0 = b.aux_off[p]; q.a1 = b.aux_off[p + 1];
+        for (int x = q.a0; x < q.a1; x++) {
+            const uint32_t pos = q.aux_pos[x];
+            const int idx = pos > 0 ? (int)pos - 1 : 0;
+            if (idx < 64) q.aux_lo |= 1ull << idx; else if (idx < 128) q.aux_hi |= 1ull << (idx - 64);
+        }
+    }
     const int sp = b.psm_spec[p];
     const int64_t off = b.spec_off[sp] - b.spec_base;
-    const float* pm = b.rmz + off;
-    const uint8_t* pr = b.rrank + off;
-    const int R = b.rcount[sp];
-    const uint8_t* ctab = b.ctab + (size_t)sp * PA_NCELL;
-    const float2 chead = b.chead[sp];
+    AscPeaks pk;
+    pk.pm = b.rmz + off; pk.pr = b.rrank + off; pk.R = b.rcount[sp];
+    pk.ctab = b.ctab + (size_t)sp * PA_NCELL;
+    { const float2 chead = b.chead[sp]; pk.cbase = chead.x; pk.cinv = chead.y; }
 
     const uint32_t best = a.best_idx[p];
     const uint64_t best_bits = pa_unrank(cfg.binom, S, k, best);
     uint64_t rem = best_bits;
     for (int jj = 0; jj < j; jj++) rem &= rem - 1;
     const int site = __ffsll((long long)rem) - 1;
-    // site index -> residue position (sites are the modifiable residues N->C)
-    int site_res[64];
+    // residue mask of the best isoform and position of the site this entry is about
+    uint64_t alo = 0, ahi = 0;
+    int pos_site = 0;
     {
         int n = 0;
         for (int i = 0; i < q.L && n < 64; i++) {
             const int c = (int)q.pep[i] - 'A';
             const bool is = ((cfg.mod_letters >> c) & 1u) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == q.L - 1);
-            if (is) site_res[n++] = i;
+            if (!is) continue;
+            if ((best_bits >> n) & 1ull) { if (i < 64) alo |= 1ull << i; else ahi |= 1ull << (i - 64); }
+            if (n == site) pos_site = i;
+            n++;
         }
-    }
-    uint64_t alo = 0, ahi = 0;
-    for (uint64_t bb = best_bits; bb; bb &= bb - 1) {
-        const int pos = site_res[__ffsll((long long)bb) - 1];
-        if (pos < 64) alo |= 1ull << pos; else ahi |= 1ull << (pos - 64);
     }
     float scA[PA_N_TOP];
     pa_depth_scores(cfg, a.iso.lo[ib + best], a.iso.hi[ib + best], (int)a.iso.nfrag[ib + best], scA);
     const float wA = a.iso.w[ib + best];
 
-    bool generic = (q.L < 2);
+    bool generic = (q.L < 2) || (NQ <= 4 && (cfg.has_nl || q.Z > NQ));
     float asc = __int_as_float(0x7f800000);
     for (uint64_t tt = a.tie[t]; tt && !generic; tt &= tt - 1) {
         const int u = __ffsll((long long)tt) - 1;
@@ -1185,32 +1446,12 @@ __global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscAr
             }
             // competitor mask = best mask with the mod moved from `site` to site u
             uint64_t blo = alo, bhi = ahi;
-            { const int pos = site_res[site]; if (pos < 64) blo &= ~(1ull << pos); else bhi &= ~(1ull << (pos - 64)); }
-            { const int pos = site_res[u]; if (pos < 64) blo |= 1ull << pos; else bhi |= 1ull << (pos - 64); }
+            { const int pos = pos_site; if (pos < 64) blo &= ~(1ull << pos); else bhi &= ~(1ull << (pos - 64)); }
+            { const int pos = asc_site_pos(cfg, q, u); if (pos < 64) blo |= 1ull << pos; else bhi |= 1ull << (pos - 64); }
             int hitsA = 0, hitsB = 0, trialsA = 0, trialsB = 0;
-            for (int ti = 0; ti < cfg.n_types && !generic; ti++) {
-                const char type = cfg.types[ti];
-                const bool fwd = (type == 'b' || type == 'c');
-                double a1, a2;
-                pa_type_consts(type, a1, a2);
-                AscList A, B;
-                if (!asc_init(cfg, q, alo, ahi, fwd, a1, a2, A) || !asc_init(cfg, q, blo, bhi, fwd, a1, a2, B)) { generic = true; break; }
-                bool mono = true;
-                float x = 0.f, y = 0.f;
-                bool hx = false, hy = false;         // a popped element is pending
-                // greedy tolerance merge of cpp/ModifiedPeptide.cpp:288-316 over the two streams
-                for (;;) {
-                    if (!hx && A.left > 0) { x = asc_pop(cfg, q, alo, ahi, fwd, a1, a2, A, mono); hx = true; }
-                    if (!hy && B.left > 0) { y = asc_pop(cfg, q, blo, bhi, fwd, a1, a2, B, mono); hy = true; }
-                    if (!hx && !hy) break;
-                    if (!hy) { trialsA++; hitsA += asc_match(pm, pr, R, ctab, chead.x, chead.y, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
-                    else if (!hx) { trialsB++; hitsB += asc_match(pm, pr, R, ctab, chead.x, chead.y, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
-                    else if (fabsf(__fsub_rn(x, y)) < cfg.err) { hx = false; hy = false; }
-                    else if (x < y) { trialsA++; hitsA += asc_match(pm, pr, R, ctab, chead.x, chead.y, x, cfg.err, cfg.err_gt_half) <= depth; hx = false; }
-                    else { trialsB++; hitsB += asc_match(pm, pr, R, ctab, chead.x, chead.y, y, cfg.err, cfg.err_gt_half) <= depth; hy = false; }
-                }
-                if (!mono) generic = true;
-            }
+            for (int ti = 0; ti < cfg.n_types && !generic; ti++)
+                if (!asc_merge_type<NQ>(cfg, q, pk, cfg.types[ti], alo, ahi, blo, bhi, depth, hitsA, trialsA, hitsB, trialsB))
+                    generic = true;
             if (!generic) {
                 const float sA = __ldg(cfg.T + pa_tab_index(trialsA, hitsA, depth));
                 const float sB = __ldg(cfg.T + pa_tab_index(trialsB, hitsB, depth));
@@ -1225,6 +1466,24 @@ __global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscAr
         return;
     }
     if (a.ascores) a.ascores[a.mod_lo + t] = asc;
+}
+
+// Threads index the four class lists back to back, each class starting on a warp boundary.
+__global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = 0;
+    for (; cls < 4; cls++) {
+        const int64_t n = a.work_count[cls];
+        if (w < n) break;
+        w -= (n + 31) & ~31ll;
+        if (w < 0) return;
+    }
+    if (cls == 4) return;
+    const int64_t t = a.work_list[(int64_t)cls * a.work_cap + w];
+    if (cls == 0) asc_entry<1>(cfg, b, a, t);
+    else if (cls == 1) asc_entry<2>(cfg, b, a, t);
+    else if (cls == 2) asc_entry<4>(cfg, b, a, t);
+    else asc_entry<PA_MAXSTREAM>(cfg, b, a, t);
 }
 
 // K3c: generic (warp-cooperative, list-materialising) Ascore for the entries k_ascore queued.

@@ -16,7 +16,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "pa_kernels.cuh"
+#include "pa_probes.cuh"
 
 #define PA_VERSION 100
 #define PA_CHUNK_PSM 131072
@@ -60,7 +60,7 @@ struct Slot {                // per-stream working set
     // plan
     DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
     // K2/K3
-    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, best_idx, mod_psm, tie, generic_list, generic_count;
+    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, best_idx, mod_psm, tie, generic_list, generic_count, work_list;
     // staged outputs
     DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
     PlanTotals* h_totals = nullptr;      // pinned
@@ -70,7 +70,7 @@ struct Slot {                // per-stream working set
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lists, &lookups, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lists, &lookups, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_list, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_totals) cudaFreeHost(h_totals);
@@ -166,6 +166,37 @@ static float residue_mass_host(char c) {
 // For every state: PowerSetSum(stack, 2) of cpp/Util.cpp:89-160 -- sums of <=2 stack elements in
 // float32, sorted ascending, de-duplicated by exact equality.  Float addition commutes, so the
 // multiset fixes the result.
+// cpp/Util.cpp:89-160 (PowerSetSum): float32 sums of the subsets of `target` with at most max_depth
+// elements, generated in the reference's recursion order (each sum = parent + element), then sorted
+// and de-duplicated by exact equality.  max_depth is clamped to the target size; 0 then means "no
+// limit" because the reference compares against an unsigned max_depth - 1.
+static void power_set_sums(const std::vector<float>& target, size_t max_depth, std::vector<float>& sums) {
+    if (target.size() < max_depth) max_depth = target.size();
+    sums.clear();
+    sums.push_back(0.f);
+    // iterative form of initializeSums(target, start, depth): children are visited right after
+    // their parent is appended, exactly like the recursion
+    std::vector<std::pair<size_t, size_t>> stack;       // (next start, depth), base kept alongside
+    std::vector<float> bases;
+    stack.push_back({0, 0}); bases.push_back(0.f);
+    while (!stack.empty()) {
+        size_t& start = stack.back().first;
+        const size_t depth = stack.back().second;
+        const float base = bases.back();
+        if (start >= target.size()) { stack.pop_back(); bases.pop_back(); continue; }
+        const size_t cur = start++;
+        const float v = base + target[cur];
+        sums.push_back(v);
+        if (cur < target.size() - 1 && depth < max_depth - 1) { stack.push_back({cur + 1, depth + 1}); bases.push_back(v); }
+    }
+    std::sort(sums.begin(), sums.end());
+    sums.erase(std::unique(sums.begin(), sums.end()), sums.end());
+}
+
+// ---- neutral-loss variant table -----------------------------------------------------------------
+// State = capped multiplicity (0,1,2) of each distinct loss mass on the stack, 2 bits per mass.
+// For every state: PowerSetSum(stack, 2) of the residues' loss stack.  Only the multiset of the stack
+// matters (sums of <= 2 elements commute, and a third copy of a mass adds no new sum).
 static void build_nl_tables(const std::vector<float>& vals, std::vector<float>& sums, std::vector<uint8_t>& nvar,
                             int& nvar_cap) {
     sums.assign(256 * 16, 0.f);
@@ -180,14 +211,7 @@ static void build_nl_tables(const std::vector<float>& vals, std::vector<float>& 
         std::vector<float> stack;
         for (int v = 0; v < g; v++) for (int c = 0; c < cnt[v]; c++) stack.push_back(vals[v]);
         std::vector<float> out;
-        out.push_back(0.f);
-        for (size_t i = 0; i < stack.size(); i++) {
-            float s1 = 0.f + stack[i];
-            out.push_back(s1);
-            if (stack.size() >= 2) for (size_t j = i + 1; j < stack.size(); j++) out.push_back(s1 + stack[j]);
-        }
-        std::sort(out.begin(), out.end());
-        out.erase(std::unique(out.begin(), out.end()), out.end());
+        power_set_sums(stack, 2, out);
         if (out.size() > 16) out.resize(16);   // cannot happen for g <= 4 (1 + 4 + 10 = 15)
         nvar[st] = (uint8_t)out.size();
         for (size_t i = 0; i < out.size(); i++) sums[st * 16 + i] = out[i];
@@ -430,6 +454,11 @@ extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float
     auto init = [&]() -> int {
         CK(s->d_binom.ensure(bin.size() * sizeof(uint32_t)));
         CK(cudaMemcpy(s->d_binom.p, bin.data(), bin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        {   // z * 1.007825 as the reference forms it (cpp/ModifiedPeptide.cpp:586), in IEEE double
+            double zm[16];
+            for (int z = 0; z < 16; z++) { volatile double zd = (double)z; zm[z] = zd * 1.007825; }
+            CK(cudaMemcpyToSymbol(c_zmass, zm, sizeof(zm)));
+        }
         for (int i = 0; i < 2; i++) {
             CK(cudaStreamCreateWithFlags(&s->slot[i].st, cudaStreamNonBlocking));
             CK(cudaMallocHost(&s->slot[i].h_totals, sizeof(PlanTotals)));
@@ -581,6 +610,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     ba.rcount = sl.rcount.as<int32_t>();
     ba.ctab = sl.ctab.as<uint8_t>(); ba.chead = sl.chead.as<float2>();
     ba.bin_size = s->bin_size; ba.n_top = s->n_top;
+    ba.rindex = nullptr; ba.rbin = nullptr; ba.bounds = nullptr;
     int cap = ((std::max(max_peaks, 32) + 31) / 32) * 32;
     cap = std::min(cap, 4096);
     int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / (int64_t)PA_BIN_SLOT_BYTES(cap)));
@@ -703,8 +733,9 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     CK(sl.mod_psm.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
     CK(sl.tie.ensure((size_t)std::max<int64_t>(nm, 1) * 8));
     CK(sl.generic_list.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
-    CK(sl.generic_count.ensure(4));
-    CK(cudaMemsetAsync(sl.generic_count.p, 0, 4, st));
+    CK(sl.work_list.ensure((size_t)std::max<int64_t>(nm, 1) * 4 * 4));
+    CK(sl.generic_count.ensure(32));                 // [0] generic entries, [1..4] k_ascore work entries by class
+    CK(cudaMemsetAsync(sl.generic_count.p, 0, 32, st));
     cs.e_asc1 = next_event(s);
     if (np > 0) {
         PaSelArgs sa;
@@ -721,6 +752,8 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.g_sort = sl.g_sort.as<unsigned long long>();
         sa.mod_lo = cs.mod_lo; sa.best_idx = sl.best_idx.as<uint32_t>(); sa.mod_psm = sl.mod_psm.as<int32_t>();
         sa.tie = sl.tie.as<unsigned long long>();
+        sa.work_list = sl.work_list.as<int32_t>(); sa.work_count = sl.generic_count.as<int>() + 1;
+        sa.work_cap = std::max<int64_t>(nm, 1);
         const int wpb = 8;
         int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
         k_select<<<blocks, wpb * 32, wpb * PA_SORTCAP * sizeof(unsigned long long), st>>>(s->cfg, cs.b, sa);
@@ -735,7 +768,9 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         aa.mod_off = cs.mod_off_abs; aa.iso_off = sl.iso_off.as<int64_t>(); aa.psm_S = sl.psm_S.as<int32_t>();
         aa.iso = iso; aa.ascores = cs.o_asc; aa.generic_list = sl.generic_list.as<int32_t>();
         aa.generic_count = sl.generic_count.as<int>();
-        k_ascore<<<(unsigned)((nm + 127) / 128), 128, 0, st>>>(s->cfg, cs.b, aa);
+        aa.work_list = sl.work_list.as<int32_t>(); aa.work_count = sl.generic_count.as<int>() + 1;
+        aa.work_cap = std::max<int64_t>(nm, 1);
+        k_ascore<<<(unsigned)((nm + 128 + 127) / 128), 128, 0, st>>>(s->cfg, cs.b, aa);
         CK(cudaGetLastError());
         const int wpb = 8;
         int blocks = s->sm_count * 2;
@@ -996,8 +1031,9 @@ extern "C" int pa_format_sequence(const pa_scorer* s, const uint8_t* pep, int32_
     return (int)o.size();
 }
 
-extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_off, const double* mz,
-                              const double* inten, float* out_mz, uint8_t* out_rank, int32_t* out_count) {
+extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* spec_off, const double* mz,
+                                 const double* inten, float* out_mz, uint8_t* out_rank, int32_t* out_count,
+                                 int32_t* out_index, int32_t* out_bin, float* out_bounds) {
     if (!s || !spec_off || !mz || !inten || !out_mz || !out_rank || !out_count) return PA_ERR_ARG;
     CK(cudaSetDevice(s->device));
     if (n_spec <= 0) return PA_OK;
@@ -1005,15 +1041,19 @@ extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_
     Slot& sl = s->slot[0];
     cudaStream_t st = sl.st;
     const int64_t lo = spec_off[0], npk = spec_off[n_spec] - lo;
+    const size_t npk1 = (size_t)std::max<int64_t>(npk, 1);
     int64_t dummy = 0;
     const int64_t* v_off; const double *v_mz, *v_int;
     CK(stage_in(sl.spec_off, spec_off, false, 0, n_spec + 1, st, &v_off, &dummy));
     CK(stage_in(sl.mz, mz, false, lo, npk, st, &v_mz, &dummy));
     CK(stage_in(sl.inten, inten, false, lo, npk, st, &v_int, &dummy));
-    CK(sl.rmz.ensure((size_t)std::max<int64_t>(npk, 1) * 4)); CK(sl.rrank.ensure((size_t)std::max<int64_t>(npk, 1)));
-    CK(sl.g_bin.ensure((size_t)std::max<int64_t>(npk, 1) * 4)); CK(sl.g_tmp.ensure((size_t)std::max<int64_t>(npk, 1)));
+    CK(sl.rmz.ensure(npk1 * 4)); CK(sl.rrank.ensure(npk1));
+    CK(sl.g_bin.ensure(npk1 * 4)); CK(sl.g_tmp.ensure(npk1));
     CK(sl.rcount.ensure((size_t)n_spec * 4));
     CK(sl.ctab.ensure((size_t)n_spec * PA_NCELL)); CK(sl.chead.ensure((size_t)n_spec * sizeof(float2)));
+    const bool extra = out_index || out_bin || out_bounds;
+    DevBuf d_index, d_bin, d_bounds;
+    if (extra) { CK(d_index.ensure(npk1 * 4)); CK(d_bin.ensure(npk1 * 4)); CK(d_bounds.ensure((size_t)n_spec * 12)); }
     int64_t m = 0;
     for (int64_t q = 0; q < n_spec; q++) m = std::max<int64_t>(m, spec_off[q + 1] - spec_off[q]);
     PaBinArgs ba;
@@ -1022,6 +1062,9 @@ extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_
     ba.g_bin = sl.g_bin.as<int32_t>() - lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - lo;
     ba.rcount = sl.rcount.as<int32_t>(); ba.bin_size = s->bin_size; ba.n_top = s->n_top;
     ba.ctab = sl.ctab.as<uint8_t>(); ba.chead = sl.chead.as<float2>();
+    ba.rindex = extra ? d_index.as<int32_t>() - lo : nullptr;
+    ba.rbin = extra ? d_bin.as<int32_t>() - lo : nullptr;
+    ba.bounds = extra ? d_bounds.as<float>() : nullptr;
     int cap = (int)std::min<int64_t>(((std::max<int64_t>(m, 32) + 31) / 32) * 32, 4096);
     int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / (int64_t)PA_BIN_SLOT_BYTES(cap)));
     ba.cap = cap;
@@ -1031,8 +1074,154 @@ extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_
     CK(cudaMemcpyAsync(out_mz + lo, sl.rmz.p, (size_t)npk * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_rank + lo, sl.rrank.p, (size_t)npk, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_count, sl.rcount.p, (size_t)n_spec * 4, cudaMemcpyDeviceToHost, st));
+    if (out_index) CK(cudaMemcpyAsync(out_index + lo, d_index.p, (size_t)npk * 4, cudaMemcpyDeviceToHost, st));
+    if (out_bin) CK(cudaMemcpyAsync(out_bin + lo, d_bin.p, (size_t)npk * 4, cudaMemcpyDeviceToHost, st));
+    if (out_bounds) CK(cudaMemcpyAsync(out_bounds, d_bounds.p, (size_t)n_spec * 12, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    d_index.release(); d_bin.release(); d_bounds.release();
     return PA_OK;
+}
+
+extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_off, const double* mz,
+                              const double* inten, float* out_mz, uint8_t* out_rank, int32_t* out_count) {
+    return pa_bin_spectra_ex(s, n_spec, spec_off, mz, inten, out_mz, out_rank, out_count, nullptr, nullptr, nullptr);
+}
+
+// ---- single-peptide probes ------------------------------------------------------------------------
+// One peptide (+ fixed mods) staged as a 1-PSM chunk without a spectrum, for the probe kernels.
+struct ProbePsm {
+    DevBuf buf;
+    PaBatchDev b;
+};
+
+static int stage_probe_psm(pa_scorer* s, const uint8_t* pep, int32_t len, const uint32_t* aux_pos,
+                           const float* aux_mass, int32_t n_aux, int32_t max_charge, ProbePsm& pp) {
+    if (len < 1 || len > PA_MAX_PEPTIDE) return fail(s, PA_ERR_UNSUPPORTED, "peptide length must be 1..%d", PA_MAX_PEPTIDE);
+    for (int i = 0; i < len; i++)
+        if (pep[i] < 'A' || pep[i] > 'Z' || std::isnan(residue_mass_host((char)pep[i])))
+            return fail(s, PA_ERR_ARG, "unknown residue letter '%c'", pep[i]);
+    for (int a = 0; a < n_aux; a++)
+        if (aux_pos[a] > (uint32_t)len) return fail(s, PA_ERR_ARG, "fixed-mod position %u beyond the peptide", aux_pos[a]);
+    int rc = refresh_config(s);
+    if (rc != PA_OK) return rc;
+    // layout: pep_off i32[2] | n_mod i32 | max_charge i32 | aux_off i32[2] | psm_spec i32 | pad | aux_pos | aux_mass | pep
+    const size_t n_aux1 = (size_t)std::max(n_aux, 1);
+    std::vector<unsigned char> h(32 + n_aux1 * 8 + (size_t)len + 8, 0);
+    int32_t* hi = (int32_t*)h.data();
+    hi[0] = 0; hi[1] = len; hi[2] = 0; hi[3] = max_charge; hi[4] = 0; hi[5] = n_aux; hi[6] = 0;
+    if (n_aux > 0) { memcpy(h.data() + 32, aux_pos, (size_t)n_aux * 4); memcpy(h.data() + 32 + n_aux1 * 4, aux_mass, (size_t)n_aux * 4); }
+    memcpy(h.data() + 32 + n_aux1 * 8, pep, (size_t)len);
+    CK(pp.buf.ensure(h.size()));
+    CK(cudaMemcpy(pp.buf.p, h.data(), h.size(), cudaMemcpyHostToDevice));
+    unsigned char* d = pp.buf.as<unsigned char>();
+    memset(&pp.b, 0, sizeof(pp.b));
+    pp.b.pep_off = (const int32_t*)d; pp.b.n_mod = (const int32_t*)(d + 8); pp.b.max_charge = (const int32_t*)(d + 12);
+    pp.b.aux_off = (const int32_t*)(d + 16); pp.b.psm_spec = (const int32_t*)(d + 24);
+    pp.b.aux_pos = (const uint32_t*)(d + 32); pp.b.aux_mass = (const float*)(d + 32 + n_aux1 * 4);
+    pp.b.pep = d + 32 + n_aux1 * 8;
+    return PA_OK;
+}
+
+extern "C" int pa_fragment_table(pa_scorer* s, const uint8_t* pep, int32_t len, const uint32_t* aux_pos,
+                                 const float* aux_mass, int32_t n_aux, uint64_t sig, char fragment_type,
+                                 int32_t charge, float* out_mz, int32_t* out_nvar) {
+    if (!s || !pep || !out_mz || !out_nvar || (n_aux > 0 && (!aux_pos || !aux_mass))) return PA_ERR_ARG;
+    if (!strchr("bcyzZ", fragment_type) || fragment_type == 0) return fail(s, PA_ERR_ARG, "fragment type not in \"bcyzZ\"");
+    if (charge < 0) return fail(s, PA_ERR_ARG, "negative charge");
+    CK(cudaSetDevice(s->device));
+    ProbePsm pp;
+    int rc = stage_probe_psm(s, pep, len, aux_pos, aux_mass, n_aux, std::max(charge, 1), pp);
+    if (rc != PA_OK) return rc;
+    DevBuf d_mz, d_nv;
+    CK(d_mz.ensure((size_t)len * 16 * 4)); CK(d_nv.ensure((size_t)len * 4));
+    CK(cudaMemset(d_mz.p, 0, (size_t)len * 16 * 4));
+    PaFragArgs a;
+    a.sig = sig; a.type = fragment_type; a.charge = charge; a.out_mz = d_mz.as<float>(); a.out_nvar = d_nv.as<int32_t>();
+    k_fragment_table<<<1, 32, sizeof(PsmSmem)>>>(s->cfg, pp.b, a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_mz, d_mz.p, (size_t)len * 16 * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_nvar, d_nv.p, (size_t)len * 4, cudaMemcpyDeviceToHost));
+    d_mz.release(); d_nv.release(); pp.buf.release();
+    return PA_OK;
+}
+
+extern "C" int pa_site_determining_ions(pa_scorer* s, const uint8_t* pep, int32_t len, const uint32_t* aux_pos,
+                                        const float* aux_mass, int32_t n_aux, uint64_t sig_a, uint64_t sig_b,
+                                        char fragment_type, int32_t max_charge, float* out_a, int32_t* n_a,
+                                        float* out_b, int32_t* n_b, int32_t cap) {
+    if (!s || !pep || !out_a || !out_b || !n_a || !n_b || (n_aux > 0 && (!aux_pos || !aux_mass))) return PA_ERR_ARG;
+    if (!strchr("bcyzZ", fragment_type) || fragment_type == 0) return fail(s, PA_ERR_ARG, "fragment type not in \"bcyzZ\"");
+    if (max_charge < 1) return fail(s, PA_ERR_ARG, "max_charge must be >= 1");
+    CK(cudaSetDevice(s->device));
+    ProbePsm pp;
+    int rc = stage_probe_psm(s, pep, len, aux_pos, aux_mass, n_aux, max_charge, pp);
+    if (rc != PA_OK) return rc;
+    const long long per_type = (long long)(len > 1 ? len - 1 : 1) * s->cfg.nvar_cap * max_charge;
+    if (per_type > (1 << 20)) return fail(s, PA_ERR_UNSUPPORTED, "fragment list too long");
+    PaSdiArgs a;
+    a.sig_a = sig_a; a.sig_b = sig_b; a.type = fragment_type; a.max_charge = max_charge;
+    a.list_stride = 32;
+    while (a.list_stride < per_type) a.list_stride <<= 1;
+    DevBuf d_a, d_b, d_cnt, d_lists;
+    CK(d_a.ensure((size_t)a.list_stride * 4)); CK(d_b.ensure((size_t)a.list_stride * 4)); CK(d_cnt.ensure(8));
+    if (per_type > PA_LCAP) CK(d_lists.ensure((size_t)4 * a.list_stride * sizeof(float)));
+    a.out_a = d_a.as<float>(); a.out_b = d_b.as<float>(); a.counts = d_cnt.as<int32_t>(); a.g_lists = d_lists.as<float>();
+    CK(cudaFuncSetAttribute(k_sdi_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    k_sdi_probe<<<1, 32, sizeof(SelSmem)>>>(s->cfg, pp.b, a);
+    CK(cudaGetLastError());
+    int32_t cnt[2];
+    CK(cudaMemcpy(cnt, d_cnt.p, 8, cudaMemcpyDeviceToHost));
+    *n_a = cnt[0]; *n_b = cnt[1];
+    if (std::min(cnt[0], cap) > 0) CK(cudaMemcpy(out_a, d_a.p, (size_t)std::min(cnt[0], cap) * 4, cudaMemcpyDeviceToHost));
+    if (std::min(cnt[1], cap) > 0) CK(cudaMemcpy(out_b, d_b.p, (size_t)std::min(cnt[1], cap) * 4, cudaMemcpyDeviceToHost));
+    d_a.release(); d_b.release(); d_cnt.release(); d_lists.release(); pp.buf.release();
+    return PA_OK;
+}
+
+extern "C" int pa_log_math(pa_scorer* s, int32_t op, int32_t n, const float* x, const float* y, const int32_t* k,
+                           const int32_t* tr, float prob, float* out) {
+    if (!s || !out || n < 0 || op < 0 || op > 4) return PA_ERR_ARG;
+    if (op == 0 ? (!x || !y) : (!k || !tr)) return PA_ERR_ARG;
+    if (n == 0) return PA_OK;
+    CK(cudaSetDevice(s->device));
+    int max_tr = 0;
+    if (op > 0)
+        for (int i = 0; i < n; i++) {
+            if (k[i] < 0 || tr[i] < 0 || k[i] > tr[i]) return fail(s, PA_ERR_ARG, "successes %d / trials %d out of range", k[i], tr[i]);
+            max_tr = std::max(max_tr, tr[i]);
+        }
+    if (max_tr > 65535) return fail(s, PA_ERR_UNSUPPORTED, "trials beyond 65535 (the reference packs (k, n) in 2 x 16 bits)");
+    std::vector<double> logd(max_tr + 2);
+    logd[0] = 0.;
+    for (int m = 1; m <= max_tr + 1; m++) logd[m] = std::log((double)m);
+    DevBuf d_in0, d_in1, d_logd, d_out;
+    CK(d_in0.ensure((size_t)n * 4)); CK(d_in1.ensure((size_t)n * 4)); CK(d_out.ensure((size_t)n * 4));
+    CK(d_logd.ensure(logd.size() * 8));
+    CK(cudaMemcpy(d_in0.p, op == 0 ? (const void*)x : (const void*)k, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_in1.p, op == 0 ? (const void*)y : (const void*)tr, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_logd.p, logd.data(), logd.size() * 8, cudaMemcpyHostToDevice));
+    PaMathArgs a;
+    a.op = op; a.n = n; a.x = d_in0.as<float>(); a.y = d_in1.as<float>(); a.k = d_in0.as<int32_t>(); a.tr = d_in1.as<int32_t>();
+    a.logd = d_logd.as<double>(); a.out = d_out.as<float>();
+    // cpp/Util.cpp:52-55 with the platform libm, as the scorer itself does
+    a.lps = logf(prob);
+    a.lpf = (float)std::log(1. - (double)prob);
+    volatile double one = 1.0;
+    a.log10e = std::log10(std::exp(one));
+    k_math_probe<<<(n + 127) / 128, 128>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, d_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    d_in0.release(); d_in1.release(); d_logd.release(); d_out.release();
+    return PA_OK;
+}
+
+extern "C" int64_t pa_power_set_sums(const float* target, int32_t n, int32_t max_depth, float* out, int64_t cap) {
+    if (n < 0 || max_depth < 0 || (n > 0 && !target)) return PA_ERR_ARG;
+    if (n > 24) return PA_ERR_UNSUPPORTED;
+    std::vector<float> t(target, target + n), sums;
+    power_set_sums(t, (size_t)max_depth, sums);
+    for (int64_t i = 0; i < (int64_t)sums.size() && i < cap; i++) out[i] = sums[i];
+    return (int64_t)sums.size();
 }
 
 extern "C" int pa_tail_table(pa_scorer* s, int32_t n_max, float* out) {
