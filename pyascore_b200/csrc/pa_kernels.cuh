@@ -1090,150 +1090,6 @@ __device__ __forceinline__ float asc_res(const PaCfg& cfg, const AscPep& q, int 
     return m;
 }
 
-// Streams of one isoform for one ion type.  NQ <= 4: everything lives in registers (loops are
-// unrolled and a stream is addressed by compare-and-select); NQ = PA_MAXSTREAM: dynamic indexing.
-template <int NQ>
-struct AscList {
-    float run[NQ];
-    float val[NQ];
-    float sigma[NQ];
-    int step[NQ];
-    int zq[NQ];
-    int nq;                      // number of streams
-    int left;                    // elements not yet popped
-};
-
-// returns false when the shape is not supported by the streaming formulation
-template <int NQ>
-__device__ __forceinline__ bool asc_init(const PaCfg& cfg, const AscPep& q, uint64_t mlo, uint64_t mhi, bool fwd,
-                                         double a1, double a2, AscList<NQ>& ls) {
-    const int L = q.L, Z = q.Z, steps = L - 1;
-    if (NQ <= 4) {
-        // no neutral loss: one stream per charge, present from the first residue on
-        const int i = fwd ? 0 : L - 1;
-        const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-        int idx;
-        const float r0 = asc_res(cfg, q, i, st, idx);
-        const double d = __dsub_rn(__dadd_rn((double)r0, a1), a2);
-        ls.nq = Z; ls.left = Z * steps;
-#pragma unroll
-        for (int z = 0; z < NQ; z++) {
-            ls.run[z] = r0; ls.sigma[z] = 0.f; ls.step[z] = 0; ls.zq[z] = z + 1;
-            ls.val[z] = (z < Z) ? pa_charge_mz(d, z + 1) : __int_as_float(0x7f800000);
-        }
-        return true;
-    } else {
-        float sig[PA_MAXSTREAM], run_at[PA_MAXSTREAM];
-        int start[PA_MAXSTREAM];
-        int V = 1;
-        if (!cfg.has_nl) {
-            if (Z > PA_MAXSTREAM) return false;
-            const int i = fwd ? 0 : L - 1;
-            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-            int idx;
-            sig[0] = 0.f; start[0] = 0;
-            run_at[0] = asc_res(cfg, q, i, st, idx);
-        } else {
-            // pass 1: the final neutral-loss state says which sums will ever exist
-            int nls = 0;
-            for (int step = 0; step < steps; step++) {
-                const int i = fwd ? step : L - 1 - step;
-                const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-                int idx;
-                (void)asc_res(cfg, q, i, st, idx);
-                if (idx) nls = pa_nl_bump(nls, idx);
-            }
-            V = cfg.nl_nvar[nls];
-            if (V * Z > PA_MAXSTREAM) return false;
-            for (int v = 0; v < V; v++) { sig[v] = __ldg(cfg.nl_sums + nls * 16 + v); start[v] = -1; run_at[v] = 0.f; }
-            // pass 2: the step at which each sum first becomes available (the stack only grows, so
-            // it stays available afterwards) and the running sum there
-            int started = 0;
-            float run = 0.f;
-            nls = 0;
-            for (int step = 0; step < steps && started < V; step++) {
-                const int i = fwd ? step : L - 1 - step;
-                const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-                int idx;
-                const float r = asc_res(cfg, q, i, st, idx);
-                run = (step == 0) ? r : __fadd_rn(r, run);
-                const int before = nls;
-                if (idx) nls = pa_nl_bump(nls, idx);
-                if (step == 0 || nls != before) {
-                    const int nv = cfg.nl_nvar[nls];
-                    for (int v = 0; v < V; v++) {
-                        if (start[v] >= 0) continue;
-                        bool in = false;
-                        for (int u = 0; u < nv; u++) in |= (__ldg(cfg.nl_sums + nls * 16 + u) == sig[v]);
-                        if (in) { start[v] = step; run_at[v] = run; started++; }
-                    }
-                }
-            }
-        }
-        ls.nq = 0; ls.left = 0;
-        for (int v = 0; v < V; v++) {
-            if (cfg.has_nl && start[v] < 0) continue;     // cannot happen: every final sum appears somewhere
-            for (int z = 1; z <= Z; z++) {
-                const int qi = ls.nq++;
-                ls.run[qi] = run_at[v]; ls.sigma[qi] = sig[v]; ls.step[qi] = start[v]; ls.zq[qi] = z;
-                const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run_at[v], sig[v]), a1), a2);
-                ls.val[qi] = pa_charge_mz(d, z);
-                ls.left += steps - start[v];
-            }
-        }
-        return true;
-    }
-}
-
-// pop the smallest pending fragment of the list; `mono` is cleared if a stream ever decreases
-template <int NQ>
-__device__ __forceinline__ float asc_pop(const PaCfg& cfg, const AscPep& q, uint64_t mlo, uint64_t mhi, bool fwd,
-                                         double a1, double a2, AscList<NQ>& ls, bool& mono) {
-    const int L = q.L, steps = L - 1;
-    const float PINF = __int_as_float(0x7f800000);
-    int bq = 0;
-    float x = ls.val[0];
-    if (NQ <= 4) {
-        float runb = ls.run[0];
-        int stepb = ls.step[0];
-#pragma unroll
-        for (int i = 1; i < NQ; i++) { const float v = ls.val[i]; if (v < x) { x = v; bq = i; runb = ls.run[i]; stepb = ls.step[i]; } }
-        const int step = stepb + 1;
-        ls.left--;
-        float nv = PINF, run = runb;
-        if (step < steps) {
-            const int i = fwd ? step : L - 1 - step;
-            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-            int idx;
-            run = __fadd_rn(asc_res(cfg, q, i, st, idx), runb);
-            const double d = __dsub_rn(__dadd_rn((double)run, a1), a2);     // sigma == 0: run - 0 == run
-            nv = pa_charge_mz(d, bq + 1);
-            if (nv < x) mono = false;
-        }
-#pragma unroll
-        for (int i = 0; i < NQ; i++) if (i == bq) { ls.run[i] = run; ls.step[i] = step; ls.val[i] = nv; }
-        return x;
-    } else {
-        for (int i = 1; i < ls.nq; i++) { const float v = ls.val[i]; if (v < x) { x = v; bq = i; } }
-        const int step = ls.step[bq] + 1;
-        ls.step[bq] = step;
-        ls.left--;
-        if (step < steps) {
-            const int i = fwd ? step : L - 1 - step;
-            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-            int idx;
-            const float r = asc_res(cfg, q, i, st, idx);
-            const float run = __fadd_rn(r, ls.run[bq]);
-            ls.run[bq] = run;
-            const double d = __dsub_rn(__dadd_rn((double)__fsub_rn(run, ls.sigma[bq]), a1), a2);
-            const float nv = pa_charge_mz(d, ls.zq[bq]);
-            if (nv < x) mono = false;
-            ls.val[bq] = nv;
-        } else ls.val[bq] = PINF;
-        return x;
-    }
-}
-
 __device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int R, const uint8_t* ctab, float cbase,
                                          float cinv, float f, float err, int err_gt_half) {
     const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
@@ -1263,6 +1119,138 @@ __device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int
 struct AscPeaks {
     const float* pm; const uint8_t* pr; int R; const uint8_t* ctab; float cbase, cinv;
 };
+
+// ---- general stream form (neutral losses and/or more than four charges) ---------------------
+// Per thread up to PA_MAXSTREAM streams per list, one per (neutral-loss sum, charge); their state
+// lives in shared memory ([field][list][stream][thread]: conflict-free) so that a stream can be
+// addressed by a run-time index without spilling to local memory.
+#define ASC_BLOCK 128
+struct AscSm {
+    float run[2][PA_MAXSTREAM][ASC_BLOCK];     // float32 running sum at the stream's current step
+    float val[2][PA_MAXSTREAM][ASC_BLOCK];     // pending fragment m/z (+inf: exhausted)
+    float sig[2][PA_MAXSTREAM][ASC_BLOCK];     // neutral-loss sum of the stream
+    int stz[2][PA_MAXSTREAM][ASC_BLOCK];       // current step | charge << 16
+};
+
+// Streams of list w (mask mlo/mhi).  Returns the stream count, or -1 when the shape is not supported.
+__device__ __forceinline__ int asc_streams_init(const PaCfg& cfg, const AscPep& q, AscSm* sm, int w, uint64_t mlo,
+                                                uint64_t mhi, bool fwd, double a1, double a2, int& left) {
+    const int tid = threadIdx.x;
+    const int L = q.L, Z = q.Z, steps = L - 1;
+    int V = 1;
+    if (!cfg.has_nl) {
+        if (Z > PA_MAXSTREAM) return -1;
+        const int i = fwd ? 0 : L - 1;
+        int idx;
+        sm->sig[w][0][tid] = 0.f; sm->stz[w][0][tid] = 0;
+        sm->run[w][0][tid] = asc_res(cfg, q, i, (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull), idx);
+    } else {
+        // pass 1: the final neutral-loss state says which sums will ever exist
+        int nls = 0;
+        for (int step = 0; step < steps; step++) {
+            const int i = fwd ? step : L - 1 - step;
+            int idx;
+            (void)asc_res(cfg, q, i, (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull), idx);
+            if (idx) nls = pa_nl_bump(nls, idx);
+        }
+        V = cfg.nl_nvar[nls];
+        if (V * Z > PA_MAXSTREAM) return -1;
+        for (int v = 0; v < V; v++) { sm->sig[w][v][tid] = __ldg(cfg.nl_sums + nls * 16 + v); sm->stz[w][v][tid] = -1; sm->run[w][v][tid] = 0.f; }
+        // pass 2: the step at which each sum first becomes available (the stack only grows, so it
+        // stays available afterwards) and the running sum there
+        int started = 0;
+        float run = 0.f;
+        nls = 0;
+        for (int step = 0; step < steps && started < V; step++) {
+            const int i = fwd ? step : L - 1 - step;
+            int idx;
+            run = __fadd_rn(asc_res(cfg, q, i, (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull), idx), run);
+            const int before = nls;
+            if (idx) nls = pa_nl_bump(nls, idx);
+            if (step == 0 || nls != before) {
+                const int nv = cfg.nl_nvar[nls];
+                for (int v = 0; v < V; v++) {
+                    if (sm->stz[w][v][tid] >= 0) continue;
+                    const float sg = sm->sig[w][v][tid];
+                    bool in = false;
+                    for (int u = 0; u < nv; u++) in |= (__ldg(cfg.nl_sums + nls * 16 + u) == sg);
+                    if (in) { sm->stz[w][v][tid] = step; sm->run[w][v][tid] = run; started++; }
+                }
+            }
+        }
+    }
+    // expand variant v into its Z charge streams v*Z .. v*Z+Z-1, back to front (slot v is read
+    // before a lower-numbered variant's stream can overwrite it)
+    left = 0;
+    for (int qi = V * Z - 1; qi >= 0; qi--) {
+        const int v = qi / Z, z = qi - v * Z + 1;
+        const float run = sm->run[w][v][tid], sg = sm->sig[w][v][tid];
+        const int start = sm->stz[w][v][tid] & 0xffff;
+        sm->run[w][qi][tid] = run; sm->sig[w][qi][tid] = sg; sm->stz[w][qi][tid] = start | (z << 16);
+        sm->val[w][qi][tid] = pa_charge_mz(__dsub_rn(__dadd_rn((double)__fsub_rn(run, sg), a1), a2), z);
+        left += steps - start;
+    }
+    return V * Z;
+}
+
+__device__ __forceinline__ bool asc_merge_streams(const PaCfg& cfg, const AscPep& q, const AscPeaks& pk, bool fwd,
+                                                  double a1, double a2, uint64_t alo, uint64_t ahi, uint64_t blo,
+                                                  uint64_t bhi, int depth, int& hitsA, int& trialsA, int& hitsB,
+                                                  int& trialsB) {
+    extern __shared__ __align__(16) unsigned char asc_smem_raw[];
+    AscSm* sm = (AscSm*)asc_smem_raw;
+    const int tid = threadIdx.x;
+    const int L = q.L, steps = L - 1;
+    const float PINF = __int_as_float(0x7f800000);
+    int leftA, leftB;
+    const int nqA = asc_streams_init(cfg, q, sm, 0, alo, ahi, fwd, a1, a2, leftA);
+    const int nqB = asc_streams_init(cfg, q, sm, 1, blo, bhi, fwd, a1, a2, leftB);
+    if (nqA < 0 || nqB < 0) return false;
+    bool mono = true;
+    float x = 0.f, y = 0.f;
+    bool hx = false, hy = false;
+    for (;;) {
+        const bool needA = !hx && leftA > 0, needB = !hy && leftB > 0;
+        if (needA || needB) {
+            const int w = needA ? 0 : 1;
+            const int nq = w ? nqB : nqA;
+            int bq = 0;
+            float xm = sm->val[w][0][tid];
+            for (int i = 1; i < nq; i++) { const float v = sm->val[w][i][tid]; if (v < xm) { xm = v; bq = i; } }
+            const int stz = sm->stz[w][bq][tid];
+            const int step = (stz & 0xffff) + 1, z = stz >> 16;
+            float nv = PINF;
+            if (step < steps) {
+                const int i = fwd ? step : L - 1 - step;
+                const uint64_t mlo = w ? blo : alo, mhi = w ? bhi : ahi;
+                int idx;
+                const float run = __fadd_rn(asc_res(cfg, q, i, (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull), idx),
+                                            sm->run[w][bq][tid]);
+                sm->run[w][bq][tid] = run;
+                nv = pa_charge_mz(__dsub_rn(__dadd_rn((double)__fsub_rn(run, sm->sig[w][bq][tid]), a1), a2), z);
+                if (nv < xm) mono = false;
+            }
+            sm->stz[w][bq][tid] = step | (z << 16);
+            sm->val[w][bq][tid] = nv;
+            if (w) { y = xm; hy = true; leftB--; } else { x = xm; hx = true; leftA--; }
+        }
+        if ((hx || leftA == 0) && (hy || leftB == 0)) {
+            if (!hx && !hy) break;
+            int takeA;                       // 1: A survives, 0: B survives, -1: both dropped
+            if (!hy) takeA = 1;
+            else if (!hx) takeA = 0;
+            else if (fabsf(__fsub_rn(x, y)) < cfg.err) takeA = -1;
+            else takeA = x < y;
+            if (takeA < 0) { hx = false; hy = false; }
+            else {
+                const int hit = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, takeA ? x : y, cfg.err, cfg.err_gt_half) <= depth;
+                if (takeA) { trialsA++; hitsA += hit; hx = false; }
+                else { trialsB++; hitsB += hit; hy = false; }
+            }
+        }
+    }
+    return mono;
+}
 
 // greedy tolerance merge of cpp/ModifiedPeptide.cpp:288-316 over the streams of the best isoform
 // (mask a) and one competitor (mask b) for one ion type; false = needs the generic kernel.
@@ -1347,23 +1335,7 @@ __device__ __forceinline__ bool asc_merge_type(const PaCfg& cfg, const AscPep& q
         }
         return mono;
     } else {
-        AscList<NQ> A, B;
-        if (!asc_init<NQ>(cfg, q, alo, ahi, fwd, a1, a2, A) || !asc_init<NQ>(cfg, q, blo, bhi, fwd, a1, a2, B)) return false;
-        for (;;) {
-            if (!hx && A.left > 0) { x = asc_pop<NQ>(cfg, q, alo, ahi, fwd, a1, a2, A, mono); hx = true; }
-            if (!hy && B.left > 0) { y = asc_pop<NQ>(cfg, q, blo, bhi, fwd, a1, a2, B, mono); hy = true; }
-            if (!hx && !hy) break;
-            int takeA;
-            if (!hy) takeA = 1;
-            else if (!hx) takeA = 0;
-            else if (fabsf(__fsub_rn(x, y)) < cfg.err) takeA = -1;
-            else takeA = x < y;
-            if (takeA < 0) { hx = false; hy = false; continue; }
-            const int rk = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, takeA ? x : y, cfg.err, cfg.err_gt_half);
-            if (takeA) { trialsA++; hitsA += rk <= depth; hx = false; }
-            else { trialsB++; hitsB += rk <= depth; hy = false; }
-        }
-        return mono;
+        return asc_merge_streams(cfg, q, pk, fwd, a1, a2, alo, ahi, blo, bhi, depth, hitsA, trialsA, hitsB, trialsB);
     }
 }
 
@@ -1422,8 +1394,8 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
             n++;
         }
     }
-    float scA[PA_N_TOP];
-    pa_depth_scores(cfg, a.iso.lo[ib + best], a.iso.hi[ib + best], (int)a.iso.nfrag[ib + best], scA);
+    const unsigned long long loA = a.iso.lo[ib + best], hiA = a.iso.hi[ib + best];
+    const int nfA = (int)a.iso.nfrag[ib + best];
     const float wA = a.iso.w[ib + best];
 
     bool generic = (q.L < 2) || (NQ <= 4 && (cfg.has_nl || q.Z > NQ));
@@ -1435,13 +1407,14 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
         const float wB = a.iso.w[ib + ci];
         float amb = 0.f;
         if (!((double)fabsf(__fsub_rn(wA, wB)) < 1e-6)) {
-            float scB[PA_N_TOP];
-            pa_depth_scores(cfg, a.iso.lo[ib + ci], a.iso.hi[ib + ci], (int)a.iso.nfrag[ib + ci], scB);
+            // depth with the largest score difference (cpp/Ascore.cpp:165-175), first strict maximum
+            const unsigned long long loB = a.iso.lo[ib + ci], hiB = a.iso.hi[ib + ci];
+            const int nfB = (int)a.iso.nfrag[ib + ci];
             float max_diff = 0.f;
             int depth = 0;
-#pragma unroll
             for (int d = 0; d < PA_N_TOP; d++) {
-                const float diff = __fsub_rn(scA[d], scB[d]);
+                const float diff = __fsub_rn(__ldg(cfg.T + pa_tab_index(nfA, pa_cum_get(loA, hiA, d), d)),
+                                             __ldg(cfg.T + pa_tab_index(nfB, pa_cum_get(loB, hiB, d), d)));
                 if (diff > max_diff) { max_diff = diff; depth = d; }
             }
             // competitor mask = best mask with the mod moved from `site` to site u
@@ -1468,22 +1441,13 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
     if (a.ascores) a.ascores[a.mod_lo + t] = asc;
 }
 
-// Threads index the four class lists back to back, each class starting on a warp boundary.
-__global__ void __launch_bounds__(128) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
-    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int cls = 0;
-    for (; cls < 4; cls++) {
-        const int64_t n = a.work_count[cls];
-        if (w < n) break;
-        w -= (n + 31) & ~31ll;
-        if (w < 0) return;
-    }
-    if (cls == 4) return;
-    const int64_t t = a.work_list[(int64_t)cls * a.work_cap + w];
-    if (cls == 0) asc_entry<1>(cfg, b, a, t);
-    else if (cls == 1) asc_entry<2>(cfg, b, a, t);
-    else if (cls == 2) asc_entry<4>(cfg, b, a, t);
-    else asc_entry<PA_MAXSTREAM>(cfg, b, a, t);
+// One launch per stream class (0: one charge, 1: two, 2: up to four, 3: neutral losses or more
+// charges), so that each instantiation gets its own register budget and occupancy.
+template <int NQ, int CLS>
+__global__ void __launch_bounds__(128, (NQ <= 2 ? 6 : 4)) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.work_count[CLS]) return;
+    asc_entry<NQ>(cfg, b, a, a.work_list[(int64_t)CLS * a.work_cap + w]);
 }
 
 // K3c: generic (warp-cooperative, list-materialising) Ascore for the entries k_ascore queued.

@@ -466,6 +466,7 @@ extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float
             CK(cudaEventCreateWithFlags(&s->slot[i].ev_plan, cudaEventDisableTiming));
         }
         CK(cudaFuncSetAttribute(k_ascore_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_ascore<PA_MAXSTREAM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm)));
         CK(cudaFuncSetAttribute(k_bin_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_tail_table, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(k_ambiguity, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -770,7 +771,14 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         aa.generic_count = sl.generic_count.as<int>();
         aa.work_list = sl.work_list.as<int32_t>(); aa.work_count = sl.generic_count.as<int>() + 1;
         aa.work_cap = std::max<int64_t>(nm, 1);
-        k_ascore<<<(unsigned)((nm + 128 + 127) / 128), 128, 0, st>>>(s->cfg, cs.b, aa);
+        const unsigned ab = (unsigned)((nm + 127) / 128);
+        if (!s->cfg.has_nl) {
+            k_ascore<1, 0><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
+            k_ascore<2, 1><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
+            k_ascore<4, 2><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
+            s->ctr.kernel_launches += 3;
+        }
+        k_ascore<PA_MAXSTREAM, 3><<<ab, ASC_BLOCK, sizeof(AscSm), st>>>(s->cfg, cs.b, aa);
         CK(cudaGetLastError());
         const int wpb = 8;
         int blocks = s->sm_count * 2;
