@@ -61,6 +61,10 @@ enum {
 int pa_create(float bin_size, int n_top, const char* mod_group, float mod_mass, float mz_error,
               const char* fragment_types, int device, pa_scorer** out);
 
+/* Replaces PyBinnedSpectra.__cinit__ (Spectra.pyx:47-48): a handle that only bins spectra
+ * (pa_bin_spectra / pa_bin_spectra_ex); any n_top in 1..254.  pa_score_batch refuses it. */
+int pa_create_binner(float bin_size, int n_top, int device, pa_scorer** out);
+
 /* Replaces PyAscore.add_neutral_loss (Ascore.pyx:81-99 -> cpp/ModifiedPeptide.cpp:99-103). */
 int pa_add_neutral_loss(pa_scorer* s, const char* group, float mass);
 

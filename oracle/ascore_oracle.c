@@ -357,20 +357,32 @@ static int power_set_sums(const float *stack, int m, float *out /* cap >= 1+m+m(
     return u;
 }
 
-long orc_power_set_sum(const float *v, size_t n, size_t depth, float *out, long cap) {
-    /* only the depth the scorer uses (2) and the degenerate smaller ones */
-    float *tmp = (float *)malloc((2 + n + n * n) * sizeof(float));
-    int m = (int)n, c;
-    if (depth >= 2 || n < 2) c = power_set_sums(v, m, tmp);
-    else {                                  /* depth 1 (or 0): singles only */
-        int q = 0; tmp[q++] = 0.f;
-        if (depth >= 1) for (int i = 0; i < m; i++) tmp[q++] = 0.f + v[i];
-        for (int i = 1; i < q; i++) { float x = tmp[i]; int j = i; while (j > 0 && tmp[j-1] > x) { tmp[j] = tmp[j-1]; j--; } tmp[j] = x; }
-        c = 1; for (int i = 1; i < q; i++) if (tmp[i] != tmp[c-1]) tmp[c++] = tmp[i];
+/* PowerSetSum::initializeSums for any max_depth (cpp/Util.cpp:99-107): children right after the
+ * parent, each sum = parent + element; the test against max_depth - 1 is unsigned there, so a
+ * max_depth of 0 (after clamping to the target size) lifts the limit. */
+static void pss_rec(const float *v, size_t n, size_t start, size_t depth, size_t max_depth, float base,
+                    float *out, long *cnt, long cap) {
+    for (; start < n; start++) {
+        float s = base + v[start];
+        if (*cnt < cap) out[*cnt] = s;
+        (*cnt)++;
+        if (start < n - 1 && depth < max_depth - 1) pss_rec(v, n, start + 1, depth + 1, max_depth, s, out, cnt, cap);
     }
-    for (int i = 0; i < c && i < cap; i++) out[i] = tmp[i];
+}
+
+long orc_power_set_sum(const float *v, size_t n, size_t depth, float *out, long cap) {
+    if (n > 20) return -1;
+    long total = 1L << n, c = 0;
+    float *tmp = (float *)malloc((size_t)(total + 1) * sizeof(float));
+    if (n < depth) depth = n;
+    tmp[c++] = 0.f;
+    pss_rec(v, n, 0, 0, depth, 0.f, tmp, &c, total + 1);
+    for (long i = 1; i < c; i++) { float x = tmp[i]; long j = i; while (j > 0 && tmp[j-1] > x) { tmp[j] = tmp[j-1]; j--; } tmp[j] = x; }
+    long u = 1;
+    for (long i = 1; i < c; i++) if (tmp[i] != tmp[u-1]) tmp[u++] = tmp[i];
+    for (long i = 0; i < u && i < cap; i++) out[i] = tmp[i];
     free(tmp);
-    return c;
+    return u;
 }
 
 /* cpp/ModifiedPeptide.cpp:570-591 */
@@ -815,8 +827,11 @@ static int peptide_string(const orc *o, uint64_t key, int have_key, char *buf, i
 }
 
 int orc_get_peptide(orc *o, size_t S, const int32_t *sig, char *buf, int cap) {
+    /* an empty signature means "the first one" (cpp/ModifiedPeptide.cpp:201-204); entries beyond
+     * the modifiable residues are ignored, missing ones count as 0, only the value 1 marks a mod */
+    if (S == 0) return peptide_string(o, 0, 0, buf, cap);
     uint64_t key = 0;
-    for (size_t i = 0; i < S; i++) key = (key << 1) | (uint64_t)(sig[i] != 0);
+    for (size_t i = 0; i < S && (int)i < o->S; i++) if (sig[i] == 1) key |= 1ull << (o->S - 1 - (int)i);
     return peptide_string(o, key, 1, buf, cap);
 }
 

@@ -5,5 +5,10 @@ there is no CPU fallback: constructing a scorer without the built .so or without
 """
 from .ascore import PyAscore
 from .batch import Scorer, format_results, pin_batch, pinned_empty
+from .ptm_scoring import (PyBinnedSpectra, PyBinomialDist, PyFragmentGraph, PyLogMath, PyModifiedPeptide,
+                          PyPowerSetSum)
+from .parsing import IdentificationParser, MassCorrector, SpectraParser
 
-__all__ = ["PyAscore", "Scorer", "format_results", "pin_batch", "pinned_empty"]
+__all__ = ["PyAscore", "Scorer", "format_results", "pin_batch", "pinned_empty", "PyBinnedSpectra", "PyBinomialDist",
+           "PyFragmentGraph", "PyLogMath", "PyModifiedPeptide", "PyPowerSetSum", "IdentificationParser",
+           "MassCorrector", "SpectraParser"]

@@ -43,7 +43,9 @@ class PaCounters(C.Structure):
 
 EXPORTS = ["pa_create", "pa_add_neutral_loss", "pa_destroy", "pa_last_error", "pa_score_batch",
            "pa_fetch_pep_scores", "pa_calculate_ambiguity", "pa_format_sequence", "pa_site_positions",
-           "pa_bin_spectra", "pa_tail_table", "pa_counters", "pa_alloc_pinned", "pa_free_pinned", "pa_version"]
+           "pa_bin_spectra", "pa_tail_table", "pa_counters", "pa_alloc_pinned", "pa_free_pinned", "pa_version",
+           "pa_create_binner", "pa_bin_spectra_ex", "pa_fragment_table", "pa_site_determining_ions", "pa_log_math",
+           "pa_power_set_sums"]
 
 _lib = None
 
@@ -87,6 +89,19 @@ def load():
     L.pa_free_pinned.restype = None
     L.pa_free_pinned.argtypes = [vp]
     L.pa_version.restype = C.c_int
+    L.pa_create_binner.restype = C.c_int
+    L.pa_create_binner.argtypes = [C.c_float, C.c_int, C.c_int, C.POINTER(vp)]
+    L.pa_bin_spectra_ex.restype = C.c_int
+    L.pa_bin_spectra_ex.argtypes = [vp, C.c_int64] + [vp] * 9
+    L.pa_fragment_table.restype = C.c_int
+    L.pa_fragment_table.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_uint64, C.c_char, C.c_int32, vp, vp]
+    L.pa_site_determining_ions.restype = C.c_int
+    L.pa_site_determining_ions.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_uint64, C.c_uint64, C.c_char,
+                                           C.c_int32, vp, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int32), C.c_int32]
+    L.pa_log_math.restype = C.c_int
+    L.pa_log_math.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_float, vp]
+    L.pa_power_set_sums.restype = C.c_int64
+    L.pa_power_set_sums.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64]
     _lib = L
     return L
 

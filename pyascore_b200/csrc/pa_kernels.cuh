@@ -1015,10 +1015,11 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 a.tie[mo + j - a.mod_lo] = tie;
                 a.mod_psm[mo + j - a.mod_lo] = (int32_t)p;
                 if (a.ascores) {
-                    // a single tied competitor within 1e-6 of the best score: Ascore 0 without looking
-                    // at any ion (cpp/Ascore.cpp:161-163); everything else is queued for k_ascore
+                    // every tied competitor has exactly the score m; within 1e-6 of the best score the
+                    // ambiguity is 0 without looking at any ion (cpp/Ascore.cpp:161-163), so the Ascore
+                    // (the minimum over the tie set) is 0.  Everything else is queued for k_ascore.
                     const float wb = a.iso.w[ib + best];
-                    if ((tie & (tie - 1)) == 0 && (double)fabsf(__fsub_rn(wb, m)) < 1e-6) a.ascores[mo + j] = 0.f;
+                    if ((double)fabsf(__fsub_rn(wb, m)) < 1e-6) a.ascores[mo + j] = 0.f;
                     else {
                         // queued by stream count so that the lanes of a k_ascore warp run the same code
                         const int Z = b.max_charge[p];

@@ -119,6 +119,7 @@ struct pa_scorer {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     int attr_set = 0;
+    bool binner_only = false;
 };
 
 static int fail(pa_scorer* s, int code, const char* fmt, ...) {
@@ -402,12 +403,12 @@ extern "C" void* pa_alloc_pinned(int64_t bytes) {
 
 extern "C" void pa_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
-extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float mod_mass, float mz_error,
-                         const char* fragment_types, int device, pa_scorer** out) {
+static int create_scorer(float bin_size, int n_top, const char* mod_group, float mod_mass, float mz_error,
+                         const char* fragment_types, int device, bool binner_only, pa_scorer** out) {
     pa_scorer* s = nullptr;
     if (!out || !mod_group || !fragment_types) return fail(nullptr, PA_ERR_ARG, "NULL argument");
     *out = nullptr;
-    if (n_top != PA_N_TOP)
+    if (binner_only ? (n_top < 1 || n_top > 254) : (n_top != PA_N_TOP))
         return fail(nullptr, PA_ERR_UNSUPPORTED, "n_top must be %d (the reference's score weights have %d entries: "
                     "smaller n_top reads out of bounds there, larger is ignored)", PA_N_TOP, PA_N_TOP);
     if (!(bin_size > 0.f)) return fail(nullptr, PA_ERR_ARG, "bin_size must be positive");
@@ -426,6 +427,7 @@ extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float
     if (e != cudaSuccess) return fail(nullptr, PA_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     s = new pa_scorer();
     s->device = device;
+    s->binner_only = binner_only;
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     s->mod_group = mod_group; s->frag_types = fragment_types;
     s->bin_size = bin_size; s->mod_mass = mod_mass; s->err = mz_error; s->n_top = n_top;
@@ -478,6 +480,15 @@ extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float
     if (rc != PA_OK) { g_create_error = s->error; pa_destroy(s); return rc; }
     *out = s;
     return PA_OK;
+}
+
+extern "C" int pa_create(float bin_size, int n_top, const char* mod_group, float mod_mass, float mz_error,
+                         const char* fragment_types, int device, pa_scorer** out) {
+    return create_scorer(bin_size, n_top, mod_group, mod_mass, mz_error, fragment_types, device, false, out);
+}
+
+extern "C" int pa_create_binner(float bin_size, int n_top, int device, pa_scorer** out) {
+    return create_scorer(bin_size, n_top, "STY", 79.966331f, 0.5f, "by", device, true, out);
 }
 
 extern "C" int pa_add_neutral_loss(pa_scorer* s, const char* group, float mass) {
@@ -811,6 +822,7 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
 extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results* out, uint32_t flags) {
     if (!s) return PA_ERR_ARG;
     if (!in || !out) return fail(s, PA_ERR_ARG, "NULL batch or results");
+    if (s->binner_only) return fail(s, PA_ERR_STATE, "this handle was made by pa_create_binner: it only bins spectra");
     if (in->n_psm < 0 || in->n_spec < 0) return fail(s, PA_ERR_ARG, "negative sizes");
     if (in->n_psm > 0 && (!in->spec_off || !in->mz || !in->inten || !in->psm_spec || !in->pep_off || !in->pep ||
                           !in->n_mod || !in->max_charge || !in->mod_off))

@@ -58,10 +58,11 @@ def test_power_set_sum_equals_reference():
     cases = [[], [18.01528], [18.01528, 18.01528], [97.9769, 18.01528, 97.9769], [1., 2., 3., 4.], [0.1, 0.2, 0.3]]
     for v in cases:
         arr = np.array(v, np.float32)
-        a, b = np.zeros(64, np.float32), np.zeros(64, np.float32)
-        na = Lr.refshim_power_set_sum(arr.ctypes.data if arr.size else None, arr.size, 2, a.ctypes.data, 64)
-        nb = Lo.refshim_power_set_sum(arr.ctypes.data if arr.size else None, arr.size, 2, b.ctypes.data, 64)
-        assert na == nb and _same(a[:na], b[:nb]), v
+        for depth in (0, 1, 2, 3, 7):       # 0: the reference's unsigned `max_depth - 1` lifts the limit
+            a, b = np.zeros(64, np.float32), np.zeros(64, np.float32)
+            na = Lr.refshim_power_set_sum(arr.ctypes.data if arr.size else None, arr.size, depth, a.ctypes.data, 64)
+            nb = Lo.refshim_power_set_sum(arr.ctypes.data if arr.size else None, arr.size, depth, b.ctypes.data, 64)
+            assert na == nb and _same(a[:na], b[:nb]), (v, depth)
 
 
 def test_all_tie_order_equals_reference():
@@ -77,3 +78,17 @@ def test_all_tie_order_equals_reference():
             O.score(mz, it, pep, k, 1)
             assert R.sequences() == O.sequences(), (ft, s, k)
             assert R.best_sequence == O.best_sequence
+
+
+def test_get_peptide_equals_reference():
+    """bracketed sequences incl. the empty-signature rule, short signatures and the overflow mod"""
+    for pep, k, aux in (("MTTTSAAAYGTHLSPHVPHRVLSTSSTLTR", 3, None), ("ASK", 3, None),
+                        ("KSTMC", 1, (np.array([0, 5], np.uint32), np.array([42.010565, 57.021464], np.float32)))):
+        R = cscorer.RefPyAscore(100., 10, "STY", 79.966331)
+        O = cscorer.OraclePyAscore(100., 10, "STY", 79.966331)
+        a = aux if aux else (None, None)
+        R.consume_peptide(pep, k, 1, *a)
+        O.consume_peptide(pep, k, 1, *a)
+        for sig in ([], [0, 1, 0, 1], [1], [0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]):
+            s = np.array(sig, np.int32)
+            assert R.get_peptide(s) == O.get_peptide(s), (pep, sig)

@@ -259,3 +259,40 @@ def test_cli_parser_and_parameter_file(tmp_path):
     for bad in (["--residues", "SB"], ["--fragment_types", "bx"], ["--max_fragment_charge", "0"]):
         with pytest.raises(ValueError):
             validate_args(p.parse_args(bad + ["s", "i", "o"]))
+
+
+# ---- PyPowerSetSum: host routine of the library (no GPU needed) --------------------------------
+def test_power_set_sum():
+    """test/test_util.py:75-96 + the oracle's restatement for random stacks"""
+    import ctypes as C
+    from oracle.cscorer import lib
+    from pyascore_b200 import PyPowerSetSum
+    pss = PyPowerSetSum()
+    assert not pss.has_next() and pss.get_sum() == 0.
+
+    def drain(p):
+        out = [p.get_sum()]
+        while p.has_next():
+            p.next()
+            out.append(p.get_sum())
+        return out
+    pss = PyPowerSetSum(np.array([1., 2., 3.], np.float32), 2)
+    assert pss.has_next() and drain(pss) == [0., 1., 2., 3., 4., 5.]
+    pss.reset(np.array([4., 5., 6.], np.float32), 2)
+    assert drain(pss) == [0., 4., 5., 6., 9., 10., 11.]
+    pss.reset()
+    assert pss.get_sum() == 0. and pss.has_next()
+    with pytest.raises(StopIteration):
+        drain(pss)
+        pss.next()
+    L = lib("orc_")._dll
+    L.orc_power_set_sum.restype = C.c_long
+    L.orc_power_set_sum.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_long]
+    rng = np.random.default_rng(11)
+    for n in range(0, 7):
+        for depth in (0, 1, 2, 3, 9):
+            t = rng.choice(np.array([18.01528, 97.9769, 17.026549, 79.966331], np.float32), n).astype(np.float32)
+            ref = np.zeros(256, np.float32)
+            m = L.orc_power_set_sum(t.ctypes.data, n, depth, ref.ctypes.data, 256)
+            got = np.array(drain(PyPowerSetSum(t, depth)), np.float32)
+            assert got.tobytes() == ref[:m].tobytes(), (n, depth, got, ref[:m])
