@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpyascore_b200.so")
+# PYASCORE_B200_LIB selects another build of the same library (tuning variants under build/)
+SO_PATH = os.environ.get("PYASCORE_B200_LIB") or os.path.join(_HERE, "libpyascore_b200.so")
 
 PA_N_TOP = 10
 PA_KEEP_ISOFORMS = 1

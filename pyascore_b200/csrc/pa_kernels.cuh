@@ -333,6 +333,7 @@ struct PaPlanOut {
     unsigned long long* combo_bits;  // [64]: bit k of row S set when (S,k) occurs with > 1 isoform
     int* max_frag;           // max fragments per isoform (all types/charges) over the chunk
     int* max_list;           // max fragments per (isoform, type) over the chunk (K3 list size)
+    int* max_len;            // longest scored peptide of the chunk (sizes K2's shared base walk)
 };
 
 __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n_psm, PaPlanOut o) {
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n
                 I = c;
                 atomicMax(o.max_frag, (int)nf);
                 atomicMax(o.max_list, (int)per_type);
+                atomicMax(o.max_len, L);
                 if (I > 1) atomicOr(&o.combo_bits[S], 1ull << k);
             }
         }
@@ -411,69 +413,87 @@ struct PaCountArgs {
     unsigned long long* n_lookups;   // counter
 };
 
-// Walk ion type `type` of the isoform with residue mask (mlo,mhi): the float32 running sum is
-// carried over every step below s1 (the reference's sequential adds), fragments are emitted and
-// matched for steps [s0, s1) only.  Returns packed non-cumulative per-rank counts; `lut[r]` holds
-// the packed increment of rank r (lut[10] = 0 for "no match").
+#ifndef PA_K2_MINBLOCKS
+#define PA_K2_MINBLOCKS 4
+#endif
+#ifndef PA_K2_UNROLL
+#define PA_K2_UNROLL 1
+#endif
+// One fragment position: every neutral-loss variant and charge of running sum `run`, matched
+// against the staged peaks; adds the packed per-rank increments (`lut[r]`, lut[10] = 0 for "no
+// match") and returns the number of fragments emitted.
+template <bool HAS_NL>
+__device__ __forceinline__ int pa_emit_step(const PaCfg& cfg, const PsmInfo& info, const float* s_nl, float run,
+                                            int nls, double a1, double a2, double zm1, double zm2,
+                                            const ulonglong2* lut, unsigned long long& clo,
+                                            unsigned long long& chi) {
+    const int Z = info.Z;
+    int nv = 1;
+    if (HAS_NL) nv = cfg.nl_nvar[nls];
+    // L == 1: the walk starts on the last residue and the reference's end test lets all but
+    // the last neutral-loss variant through (cpp/ModifiedPeptide.cpp:516-524)
+    if (info.L == 1) nv -= 1;
+    for (int v = 0; v < nv; v++) {
+        float base = run;
+        if (HAS_NL) base = __fsub_rn(run, s_nl[nls * 16 + v]);
+        const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
+        // charge z: (d + z * 1.007825) / z  (cpp/ModifiedPeptide.cpp:585-587); 1 and 2 are unrolled
+        {
+            const int rk = pa_match_rank(info, __double2float_rn(__dadd_rn(d, zm1)), cfg.err, cfg.err_gt_half);
+            const ulonglong2 inc = lut[rk < 10 ? rk : 10];
+            clo += inc.x; chi += inc.y;
+        }
+        if (Z >= 2) {
+            const int rk = pa_match_rank(info, __double2float_rn(__dmul_rn(__dadd_rn(d, zm2), 0.5)), cfg.err, cfg.err_gt_half);
+            const ulonglong2 inc = lut[rk < 10 ? rk : 10];
+            clo += inc.x; chi += inc.y;
+        }
+        for (int z = 3; z <= Z; z++) {
+            const int rk = pa_match_rank(info, pa_charge_mz(d, z), cfg.err, cfg.err_gt_half);
+            const ulonglong2 inc = lut[rk < 10 ? rk : 10];
+            clo += inc.x; chi += inc.y;
+        }
+    }
+    return nv * Z;
+}
+
+// Walk ion type `type` of the isoform with residue mask (mlo,mhi) from step `f` on, where the
+// float32 running sum / neutral-loss state before step f are (run, nls): the reference's
+// sequential adds are replayed for steps [f, s0) and fragments are emitted and matched for
+// steps [s0, s1).  Returns packed non-cumulative per-rank counts.
 template <bool HAS_NL>
 __device__ __forceinline__ void pa_walk_isoform(const PaCfg& cfg, const PsmSmem* sm, const PsmInfo& info,
-                                                uint64_t mlo, uint64_t mhi, char type, int s0, int s1,
-                                                const ulonglong2* lut, unsigned long long& clo,
-                                                unsigned long long& chi, uint32_t& nfrag) {
-    const int L = info.L, Z = info.Z;
+                                                const float* s_nl, uint64_t mlo, uint64_t mhi, char type, int f,
+                                                float run, int nls, int s0, int s1, const ulonglong2* lut,
+                                                unsigned long long& clo, unsigned long long& chi, uint32_t& nfrag) {
+    const int L = info.L;
     clo = 0; chi = 0; nfrag = 0;
     const bool fwd = (type == 'b' || type == 'c');
     double a1, a2;
     pa_type_consts(type, a1, a2);
     const double zm1 = c_zmass[1], zm2 = c_zmass[2];
-    float run = 0.f;             // r + 0.f == r: the first step needs no special case
-    int nls = 0;
     // replay: the lanes of a split walk have different s0, but this loop is cheap; the matching
     // loop below then runs in lock step over all lanes of the warp
-    for (int step = 0; step < s0; step++) {
+    for (int step = f; step < s0; step++) {
         const int i = fwd ? step : L - 1 - step;
         const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-        run = __fadd_rn(sm->res[i][st], run);
+        run = __fadd_rn(sm->res[i][st], run);          // r + 0.f == r: the first step needs no special case
         if (HAS_NL) {
             int idx = sm->nlidx[i][st];
             if (idx) nls = pa_nl_bump(nls, idx);
         }
     }
+    constexpr int kUnroll = PA_K2_UNROLL;
+#pragma unroll kUnroll
     for (int step = s0; step < s1; step++) {
         const int i = fwd ? step : L - 1 - step;
         const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
         run = __fadd_rn(sm->res[i][st], run);
-        int nv = 1;
         if (HAS_NL) {
             int idx = sm->nlidx[i][st];
             if (idx) nls = pa_nl_bump(nls, idx);
-            nv = cfg.nl_nvar[nls];
         }
-        // L == 1: the walk starts on the last residue and the reference's end test lets all but
-        // the last neutral-loss variant through (cpp/ModifiedPeptide.cpp:516-524)
-        if (L == 1) nv -= 1;
-        for (int v = 0; v < nv; v++) {
-            float base = run;
-            if (HAS_NL) base = __fsub_rn(run, __ldg(cfg.nl_sums + nls * 16 + v));
-            const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
-            // charge z: (d + z * 1.007825) / z  (cpp/ModifiedPeptide.cpp:585-587); 1 and 2 are unrolled
-            {
-                const int rk = pa_match_rank(info, __double2float_rn(__dadd_rn(d, zm1)), cfg.err, cfg.err_gt_half);
-                const ulonglong2 inc = lut[rk < 10 ? rk : 10];
-                clo += inc.x; chi += inc.y;
-            }
-            if (Z >= 2) {
-                const int rk = pa_match_rank(info, __double2float_rn(__dmul_rn(__dadd_rn(d, zm2), 0.5)), cfg.err, cfg.err_gt_half);
-                const ulonglong2 inc = lut[rk < 10 ? rk : 10];
-                clo += inc.x; chi += inc.y;
-            }
-            for (int z = 3; z <= Z; z++) {
-                const int rk = pa_match_rank(info, pa_charge_mz(d, z), cfg.err, cfg.err_gt_half);
-                const ulonglong2 inc = lut[rk < 10 ? rk : 10];
-                clo += inc.x; chi += inc.y;
-            }
-            nfrag += Z;
-        }
+        nfrag += pa_emit_step<HAS_NL>(cfg, info, s_nl, run, nls, a1, a2, zm1, zm2, lut, clo, chi);
     }
 }
 
@@ -518,14 +538,16 @@ __device__ __forceinline__ void pa_sites_to_mask(const PsmSmem* sm, uint64_t bit
 // up to its segment and matches only its own fragments), so that small PSMs still fill the warp.
 // The lanes of one isoform are contiguous and add their packed counts with xor-shuffles.
 template <bool HAS_NL, bool PAIR>
-__global__ void __launch_bounds__(256) k_count_score(PaCfg cfg, PaBatchDev b, PaCountArgs a) {
+__global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg, PaBatchDev b, PaCountArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ ulonglong2 s_lut[16];
+    __shared__ float s_nl[HAS_NL ? 256 * 16 : 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     if (threadIdx.x < 16) {
         const int r = threadIdx.x;
         s_lut[r] = make_ulonglong2(r < 5 ? 1ull << (12 * r) : 0ull, (r >= 5 && r < 10) ? 1ull << (12 * (r - 5)) : 0ull);
     }
+    if (HAS_NL) for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) s_nl[i] = cfg.nl_sums[i];
     __syncthreads();
     PsmSmem* sm = (PsmSmem*)smem_raw + wib;
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
@@ -535,9 +557,9 @@ __global__ void __launch_bounds__(256) k_count_score(PaCfg cfg, PaBatchDev b, Pa
     const int T = PAIR ? 2 : 1;
     for (int64_t u = gw; u < a.n_units; u += nw) {
         const int64_t p = a.unit_psm[u];
+        const int64_t I = a.iso_off[p + 1] - a.iso_off[p];
         if (p != cur) { pa_setup_psm(cfg, b, p, sm, info, true); cur = p; }
         const int S = a.psm_S[p], k = info.k;
-        const int64_t I = a.iso_off[p + 1] - a.iso_off[p];
         const int64_t first = (int64_t)(u - a.unit_off[p]) * PA_UNIT;
         const int cnt = (int)((I - first < PA_UNIT) ? I - first : PA_UNIT);
         const int steps = (info.L == 1) ? 1 : info.L - 1;
@@ -557,11 +579,11 @@ __global__ void __launch_bounds__(256) k_count_score(PaCfg cfg, PaBatchDev b, Pa
                 pa_sites_to_mask(sm, bits, mlo, mhi);
                 const int s0 = (steps * h) >> hs, s1 = (steps * (h + 1)) >> hs;
                 if (PAIR) {
-                    pa_walk_isoform<HAS_NL>(cfg, sm, info, mlo, mhi, cfg.types[sub >> hs], s0, s1, s_lut, clo, chi, nf);
+                    pa_walk_isoform<HAS_NL>(cfg, sm, info, s_nl, mlo, mhi, cfg.types[sub >> hs], 0, 0.f, 0, s0, s1, s_lut, clo, chi, nf);
                 } else {
                     for (int t = 0; t < cfg.n_types; t++) {
                         unsigned long long xlo, xhi; uint32_t xn;
-                        pa_walk_isoform<HAS_NL>(cfg, sm, info, mlo, mhi, cfg.types[t], s0, s1, s_lut, xlo, xhi, xn);
+                        pa_walk_isoform<HAS_NL>(cfg, sm, info, s_nl, mlo, mhi, cfg.types[t], 0, 0.f, 0, s0, s1, s_lut, xlo, xhi, xn);
                         clo += xlo; chi += xhi; nf += xn;
                     }
                 }
@@ -1444,8 +1466,11 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
 
 // One launch per stream class (0: one charge, 1: two, 2: up to four, 3: neutral losses or more
 // charges), so that each instantiation gets its own register budget and occupancy.
+#ifndef PA_ASC_MINBLOCKS
+#define PA_ASC_MINBLOCKS 6
+#endif
 template <int NQ, int CLS>
-__global__ void __launch_bounds__(128, (NQ <= 2 ? 6 : 4)) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
+__global__ void __launch_bounds__(128, (NQ <= 2 ? PA_ASC_MINBLOCKS : 4)) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.work_count[CLS]) return;
     asc_entry<NQ>(cfg, b, a, a.work_list[(int64_t)CLS * a.work_cap + w]);

@@ -48,7 +48,7 @@ struct PlanTotals {          // device -> host after planning a chunk
     int max_frag, max_list;
     long long total_iso;
     int total_units;
-    int pad;
+    int max_len;
 };
 
 struct Slot {                // per-stream working set
@@ -655,7 +655,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     po.psm_S = sl.psm_S.as<int32_t>(); po.psm_status = sl.psm_status.as<int32_t>();
     po.psm_I = sl.psm_I.as<int64_t>(); po.psm_units = sl.psm_units.as<int32_t>();
     PlanTotals* dt = sl.totals.as<PlanTotals>();
-    po.combo_bits = dt->combo_bits; po.max_frag = &dt->max_frag; po.max_list = &dt->max_list;
+    po.combo_bits = dt->combo_bits; po.max_frag = &dt->max_frag; po.max_list = &dt->max_list; po.max_len = &dt->max_len;
     if (np > 0) {
         k_plan<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(s->cfg, b, np, po);
         CK(cudaGetLastError());
@@ -719,8 +719,8 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         ca.iso = iso; ca.n_lookups = sl.lookups.as<unsigned long long>();
         const int wpb = 8;
         int blocks = (int)std::min<int64_t>(((int64_t)n_units + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
-        size_t smem = wpb * sizeof(PsmSmem);
         const bool pair = s->cfg.n_types == 2;
+        size_t smem = wpb * sizeof(PsmSmem);
         if (s->cfg.has_nl) {
             if (pair) k_count_score<true, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
             else k_count_score<true, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
