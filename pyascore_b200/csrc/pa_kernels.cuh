@@ -1467,7 +1467,7 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
 // One launch per stream class (0: one charge, 1: two, 2: up to four, 3: neutral losses or more
 // charges), so that each instantiation gets its own register budget and occupancy.
 #ifndef PA_ASC_MINBLOCKS
-#define PA_ASC_MINBLOCKS 6
+#define PA_ASC_MINBLOCKS 8
 #endif
 template <int NQ, int CLS>
 __global__ void __launch_bounds__(128, (NQ <= 2 ? PA_ASC_MINBLOCKS : 4)) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
