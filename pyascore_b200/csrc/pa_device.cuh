@@ -144,13 +144,16 @@ __device__ __forceinline__ uint64_t pa_unrank(const uint32_t* __restrict__ tab, 
     return bits;
 }
 
+// lexicographic rank of a k-subset.  The subsets that precede `bits` and first differ at its
+// i-th element c_i are those whose i-th element lies in (c_{i-1}, c_i): by the hockey-stick
+// identity their number is C(S-1-c_{i-1}, k-i) - C(S-c_i, k-i).
 __device__ __forceinline__ uint32_t pa_rank(const uint32_t* __restrict__ tab, int S, int k, uint64_t bits) {
     uint32_t r = 0;
     int prev = -1, i = 0;
     while (bits) {
         int c = __ffsll((long long)bits) - 1;
         bits &= bits - 1;
-        for (int j = prev + 1; j < c; j++) r += pa_binom(tab, S - 1 - j, k - 1 - i);
+        r += pa_binom(tab, S - 1 - prev, k - i) - pa_binom(tab, S - c, k - i);
         prev = c;
         i++;
     }
@@ -306,7 +309,9 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
 
 // rank of the best (most intense) retained peak matching theoretical fragment f, or 255.
 // cpp/ModifiedPeptide.cpp:126-142 seen from the fragment's side (SURVEY.md section 7.3 "Matching").
-__device__ __forceinline__ int pa_match_rank(const PsmInfo& info, float f, float err, int err_gt_half) {
+template <bool EGH = true>
+__device__ __forceinline__ int pa_match_rank(const PsmInfo& info, float f, float err, int err_gt_half_rt) {
+    const bool err_gt_half = EGH && err_gt_half_rt;      // EGH = false: mz_error <= 0.5, the clause cannot bind
     const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
     int best = 255;
     if (info.cell != nullptr) {

@@ -208,9 +208,13 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                         // earlier index: (kj + [j < i]) > ki covers both sides of i
                         const int b0 = s_bstart[bq], b1 = s_bend[bq];
                         const uint32_t hi = (uint32_t)(ki >> 32);
-                        int eq = 0;
-#pragma unroll 4
-                        for (int j = b0; j < b1; j++) {
+                        int eq = 0, j = b0;
+                        for (; j + 4 <= b1; j += 4) {
+                            const uint32_t h0 = s_k2[j].y, h1 = s_k2[j + 1].y, h2 = s_k2[j + 2].y, h3 = s_k2[j + 3].y;
+                            cnt += (h0 > hi) + (h1 > hi) + (h2 > hi) + (h3 > hi);
+                            eq += (h0 == hi) + (h1 == hi) + (h2 == hi) + (h3 == hi);
+                        }
+                        for (; j < b1; j++) {
                             const uint32_t h = s_k2[j].y;
                             cnt += (h > hi);
                             eq += (h == hi);
@@ -245,14 +249,34 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 __syncwarp();
                 const float cbase = s_out[0];
                 const float cinv = pa_cell_inv(cbase, s_out[out - 1]);
+                // cell[c] = first retained peak whose cell is >= c.  Mark the first peak of every
+                // occupied cell (empty = `out`), then take the suffix minimum over the 256 cells:
+                // 8 cells per lane locally, a shuffle scan across lanes.
+                ((unsigned long long*)s_cell)[lane] = 0x0101010101010101ull * (unsigned long long)out;
+                __syncwarp();
                 for (int j = lane; j < out; j += 32) {
                     const int cj = pa_cell(s_out[j], cbase, cinv);
                     const int cp = j > 0 ? pa_cell(s_out[j - 1], cbase, cinv) : -1;
-                    for (int c = cp + 1; c <= cj; c++) s_cell[c] = (uint8_t)j;
-                    if (j == out - 1) for (int c = cj + 1; c < PA_NCELL; c++) s_cell[c] = (uint8_t)out;
+                    if (cj != cp) s_cell[cj] = (uint8_t)j;
                 }
                 __syncwarp();
-                ((unsigned long long*)(a.ctab + (size_t)s * PA_NCELL))[lane] = ((const unsigned long long*)s_cell)[lane];
+                unsigned long long v = ((const unsigned long long*)s_cell)[lane];
+                unsigned bb[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) bb[t] = (unsigned)(v >> (8 * t)) & 0xffu;
+#pragma unroll
+                for (int t = 6; t >= 0; t--) bb[t] = min(bb[t], bb[t + 1]);
+                unsigned x = bb[0];                      // suffix minimum over this and the higher lanes
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned y = __shfl_down_sync(PA_FULL, x, o);
+                    if (lane + o < 32) x = min(x, y);
+                }
+                unsigned carry = __shfl_down_sync(PA_FULL, x, 1);
+                if (lane == 31) carry = (unsigned)out;
+                v = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) v |= (unsigned long long)min(bb[t], carry) << (8 * t);
+                ((unsigned long long*)(a.ctab + (size_t)s * PA_NCELL))[lane] = v;
                 if (lane == 0) a.chead[s] = make_float2(cbase, cinv);
             } else if (lane == 0) a.chead[s] = make_float2(0.f, 0.f);
         } else {
@@ -333,7 +357,9 @@ struct PaPlanOut {
     unsigned long long* combo_bits;  // [64]: bit k of row S set when (S,k) occurs with > 1 isoform
     int* max_frag;           // max fragments per isoform (all types/charges) over the chunk
     int* max_list;           // max fragments per (isoform, type) over the chunk (K3 list size)
-    int* max_len;            // longest scored peptide of the chunk (sizes K2's shared base walk)
+    int* max_len;            // longest scored peptide of the chunk
+    uint8_t* sort_key;       // [n_psm] peptide length (order in which k_select visits the PSMs)
+    int32_t* sort_idx;       // [n_psm] identity
 };
 
 __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n_psm, PaPlanOut o) {
@@ -377,6 +403,8 @@ __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n
         }
     }
     o.psm_S[p] = S;
+    o.sort_key[p] = (uint8_t)(L < 0 ? 0 : (L > 255 ? 255 : L));
+    o.sort_idx[p] = (int32_t)p;
     o.psm_status[p] = status;
     o.psm_I[p] = I;
     o.psm_units[p] = (int32_t)((I + PA_UNIT - 1) / PA_UNIT);
@@ -422,7 +450,7 @@ struct PaCountArgs {
 // One fragment position: every neutral-loss variant and charge of running sum `run`, matched
 // against the staged peaks; adds the packed per-rank increments (`lut[r]`, lut[10] = 0 for "no
 // match") and returns the number of fragments emitted.
-template <bool HAS_NL>
+template <bool HAS_NL, bool EGH>
 __device__ __forceinline__ int pa_emit_step(const PaCfg& cfg, const PsmInfo& info, const float* s_nl, float run,
                                             int nls, double a1, double a2, double zm1, double zm2,
                                             const ulonglong2* lut, unsigned long long& clo,
@@ -439,17 +467,17 @@ __device__ __forceinline__ int pa_emit_step(const PaCfg& cfg, const PsmInfo& inf
         const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
         // charge z: (d + z * 1.007825) / z  (cpp/ModifiedPeptide.cpp:585-587); 1 and 2 are unrolled
         {
-            const int rk = pa_match_rank(info, __double2float_rn(__dadd_rn(d, zm1)), cfg.err, cfg.err_gt_half);
+            const int rk = pa_match_rank<EGH>(info, __double2float_rn(__dadd_rn(d, zm1)), cfg.err, cfg.err_gt_half);
             const ulonglong2 inc = lut[rk < 10 ? rk : 10];
             clo += inc.x; chi += inc.y;
         }
         if (Z >= 2) {
-            const int rk = pa_match_rank(info, __double2float_rn(__dmul_rn(__dadd_rn(d, zm2), 0.5)), cfg.err, cfg.err_gt_half);
+            const int rk = pa_match_rank<EGH>(info, __double2float_rn(__dmul_rn(__dadd_rn(d, zm2), 0.5)), cfg.err, cfg.err_gt_half);
             const ulonglong2 inc = lut[rk < 10 ? rk : 10];
             clo += inc.x; chi += inc.y;
         }
         for (int z = 3; z <= Z; z++) {
-            const int rk = pa_match_rank(info, pa_charge_mz(d, z), cfg.err, cfg.err_gt_half);
+            const int rk = pa_match_rank<EGH>(info, pa_charge_mz(d, z), cfg.err, cfg.err_gt_half);
             const ulonglong2 inc = lut[rk < 10 ? rk : 10];
             clo += inc.x; chi += inc.y;
         }
@@ -461,7 +489,7 @@ __device__ __forceinline__ int pa_emit_step(const PaCfg& cfg, const PsmInfo& inf
 // float32 running sum / neutral-loss state before step f are (run, nls): the reference's
 // sequential adds are replayed for steps [f, s0) and fragments are emitted and matched for
 // steps [s0, s1).  Returns packed non-cumulative per-rank counts.
-template <bool HAS_NL>
+template <bool HAS_NL, bool EGH>
 __device__ __forceinline__ void pa_walk_isoform(const PaCfg& cfg, const PsmSmem* sm, const PsmInfo& info,
                                                 const float* s_nl, uint64_t mlo, uint64_t mhi, char type, int f,
                                                 float run, int nls, int s0, int s1, const ulonglong2* lut,
@@ -493,7 +521,7 @@ __device__ __forceinline__ void pa_walk_isoform(const PaCfg& cfg, const PsmSmem*
             int idx = sm->nlidx[i][st];
             if (idx) nls = pa_nl_bump(nls, idx);
         }
-        nfrag += pa_emit_step<HAS_NL>(cfg, info, s_nl, run, nls, a1, a2, zm1, zm2, lut, clo, chi);
+        nfrag += pa_emit_step<HAS_NL, EGH>(cfg, info, s_nl, run, nls, a1, a2, zm1, zm2, lut, clo, chi);
     }
 }
 
@@ -537,7 +565,7 @@ __device__ __forceinline__ void pa_sites_to_mask(const PsmSmem* sm, uint64_t bit
 // walk is further split into H segments of consecutive steps (a lane replays the cheap running sum
 // up to its segment and matches only its own fragments), so that small PSMs still fill the warp.
 // The lanes of one isoform are contiguous and add their packed counts with xor-shuffles.
-template <bool HAS_NL, bool PAIR>
+template <bool HAS_NL, bool PAIR, bool EGH>
 __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg, PaBatchDev b, PaCountArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ ulonglong2 s_lut[16];
@@ -579,11 +607,11 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
                 pa_sites_to_mask(sm, bits, mlo, mhi);
                 const int s0 = (steps * h) >> hs, s1 = (steps * (h + 1)) >> hs;
                 if (PAIR) {
-                    pa_walk_isoform<HAS_NL>(cfg, sm, info, s_nl, mlo, mhi, cfg.types[sub >> hs], 0, 0.f, 0, s0, s1, s_lut, clo, chi, nf);
+                    pa_walk_isoform<HAS_NL, EGH>(cfg, sm, info, s_nl, mlo, mhi, cfg.types[sub >> hs], 0, 0.f, 0, s0, s1, s_lut, clo, chi, nf);
                 } else {
                     for (int t = 0; t < cfg.n_types; t++) {
                         unsigned long long xlo, xhi; uint32_t xn;
-                        pa_walk_isoform<HAS_NL>(cfg, sm, info, s_nl, mlo, mhi, cfg.types[t], 0, 0.f, 0, s0, s1, s_lut, xlo, xhi, xn);
+                        pa_walk_isoform<HAS_NL, EGH>(cfg, sm, info, s_nl, mlo, mhi, cfg.types[t], 0, 0.f, 0, s0, s1, s_lut, xlo, xhi, xn);
                         clo += xlo; chi += xhi; nf += xn;
                     }
                 }
@@ -649,7 +677,8 @@ struct PaSelArgs {
     int32_t* work_list;          // [4][work_cap] entries whose Ascore needs the site-determining-ion comparison,
     int* work_count;             // [4]              by stream class (k_ascore)
     int64_t work_cap;
-};
+    const int32_t* order;        // [n_psm] PSMs by peptide length: neighbouring Ascore entries then run
+};                               //         merges of similar length, which keeps k_ascore's warps converged
 
 // --- libstdc++ std::sort (introsort + final insertion sort), comparator a.w > b.w ------------
 // bits/stl_algo.h of GCC 13, as in SURVEY.md appendix A.2.  Elements are (float w, uint32 id)
@@ -932,6 +961,23 @@ __device__ __forceinline__ void pa_depth_scores(const PaCfg& cfg, unsigned long 
     for (int d = 0; d < PA_N_TOP; d++) sc[d] = __ldg(cfg.T + pa_tab_index(n, pa_cum_get(lo, hi, d), d));
 }
 
+// append the warp's buffered Ascore entries (entry | class << 30) to the four global lists
+__device__ __forceinline__ void pa_flush_queue(const PaSelArgs& a, const uint32_t* s_queue, int qn) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    const uint32_t e = lane < qn ? s_queue[lane] : 0u;
+    for (int c = 0; c < 4; c++) {
+        const unsigned mask = __ballot_sync(PA_FULL, lane < qn && (int)(e >> 30) == c);
+        if (!mask) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.work_count + c, __popc(mask));
+        base = __shfl_sync(PA_FULL, base, 0);
+        if ((mask >> lane) & 1u)
+            a.work_list[(int64_t)c * a.work_cap + base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)(e & 0x3fffffffu);
+    }
+    __syncwarp();
+}
+
 // K3a: warp per PSM.  Best isoform in the reference's order + per modified site the set of tied
 // best competitors (= alternative sites).  The Ascore of every (PSM, site) entry is then computed
 // by k_ascore (thread per entry) or, for the rare shapes that kernel does not cover, k_ascore_generic.
@@ -939,10 +985,14 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned long long* s_sort = (unsigned long long*)smem_raw + (size_t)wib * PA_SORTCAP;
+    __shared__ uint32_t s_queue_all[8][32];
+    uint32_t* s_queue = s_queue_all[wib];
+    int qn = 0;                                       // entries buffered by this warp (lane-uniform)
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const float INF = __int_as_float(0x7f800000);
 
-    for (int64_t p = gw; p < a.n_psm; p += nw) {
+    for (int64_t pi = gw; pi < a.n_psm; pi += nw) {
+        const int64_t p = a.order ? a.order[pi] : pi;
         const int status = a.psm_status[p];
         const int k = b.n_mod[p];
         const int64_t mo = a.mod_off[p];
@@ -1039,20 +1089,28 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 if (a.ascores) {
                     // every tied competitor has exactly the score m; within 1e-6 of the best score the
                     // ambiguity is 0 without looking at any ion (cpp/Ascore.cpp:161-163), so the Ascore
-                    // (the minimum over the tie set) is 0.  Everything else is queued for k_ascore.
+                    // (the minimum over the tie set) is 0
                     const float wb = a.iso.w[ib + best];
                     if ((double)fabsf(__fsub_rn(wb, m)) < 1e-6) a.ascores[mo + j] = 0.f;
-                    else {
-                        // queued by stream count so that the lanes of a k_ascore warp run the same code
-                        const int Z = b.max_charge[p];
-                        const int cls = cfg.has_nl ? 3 : (Z == 1 ? 0 : (Z == 2 ? 1 : (Z <= 4 ? 2 : 3)));
-                        a.work_list[(int64_t)cls * a.work_cap + atomicAdd(a.work_count + cls, 1)] = (int32_t)(mo + j - a.mod_lo);
-                    }
+                }
+            }
+            if (a.ascores) {
+                // everything else is queued for k_ascore, by stream count so that the lanes of a
+                // k_ascore warp run the same code.  Entries collect in a per-warp buffer and are
+                // appended to the global lists 32 at a time (one atomic per class and flush).
+                const float wb = a.iso.w[ib + best];
+                if (!((double)fabsf(__fsub_rn(wb, m)) < 1e-6)) {
+                    if (qn == 32) { pa_flush_queue(a, s_queue, qn); qn = 0; }
+                    const int Z = b.max_charge[p];
+                    const int cls = cfg.has_nl ? 3 : (Z == 1 ? 0 : (Z == 2 ? 1 : (Z <= 4 ? 2 : 3)));
+                    if (lane == 0) s_queue[qn] = (uint32_t)(mo + j - a.mod_lo) | ((uint32_t)cls << 30);
+                    qn++;
                 }
             }
         }
         __syncwarp();
     }
+    if (a.ascores) pa_flush_queue(a, s_queue, qn);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -58,7 +58,7 @@ struct Slot {                // per-stream working set
     // K1
     DevBuf rmz, rrank, rcount, ctab, chead, g_bin, g_tmp;
     // plan
-    DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
+    DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp, sort_key, sort_idx, sort_key2, order;
     // K2/K3
     DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, best_idx, mod_psm, tie, generic_list, generic_count, work_list;
     // staged outputs
@@ -69,7 +69,7 @@ struct Slot {                // per-stream working set
     void release() {
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
-                         &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
+                         &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &sort_key, &sort_idx, &sort_key2, &order, &iso_lo, &iso_hi, &iso_n,
                          &iso_w, &g_sort, &g_lists, &lookups, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_list, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
@@ -654,6 +654,9 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     PaPlanOut po;
     po.psm_S = sl.psm_S.as<int32_t>(); po.psm_status = sl.psm_status.as<int32_t>();
     po.psm_I = sl.psm_I.as<int64_t>(); po.psm_units = sl.psm_units.as<int32_t>();
+    CK(sl.sort_key.ensure((size_t)(np + 1))); CK(sl.sort_key2.ensure((size_t)(np + 1)));
+    CK(sl.sort_idx.ensure((size_t)(np + 1) * 4)); CK(sl.order.ensure((size_t)(np + 1) * 4));
+    po.sort_key = sl.sort_key.as<uint8_t>(); po.sort_idx = sl.sort_idx.as<int32_t>();
     PlanTotals* dt = sl.totals.as<PlanTotals>();
     po.combo_bits = dt->combo_bits; po.max_frag = &dt->max_frag; po.max_list = &dt->max_list; po.max_len = &dt->max_len;
     if (np > 0) {
@@ -661,15 +664,23 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
         CK(cudaGetLastError());
         s->ctr.kernel_launches++;
     }
-    size_t t1 = 0, t2 = 0;
+    size_t t1 = 0, t2 = 0, t3 = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, t1, po.psm_I, sl.iso_off.as<int64_t>(), (int)(np + 1), st));
     CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, po.psm_units, sl.unit_off.as<int32_t>(), (int)(np + 1), st));
-    CK(sl.cub_tmp.ensure(std::max(t1, t2) + 256));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, t3, po.sort_key, sl.sort_key2.as<uint8_t>(), po.sort_idx,
+                                       sl.order.as<int32_t>(), (int)np, 0, 8, st));
+    CK(sl.cub_tmp.ensure(std::max(std::max(t1, t2), t3) + 256));
     size_t tb = sl.cub_tmp.cap;
     CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, tb, po.psm_I, sl.iso_off.as<int64_t>(), (int)(np + 1), st));
     tb = sl.cub_tmp.cap;
     CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, tb, po.psm_units, sl.unit_off.as<int32_t>(), (int)(np + 1), st));
     s->ctr.kernel_launches += 2;
+    if (np > 0) {      // PSMs by peptide length, for k_select (stable: equal lengths stay in input order)
+        tb = sl.cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(sl.cub_tmp.p, tb, po.sort_key, sl.sort_key2.as<uint8_t>(), po.sort_idx,
+                                           sl.order.as<int32_t>(), (int)np, 0, 8, st));
+        s->ctr.kernel_launches += 3;
+    }
     CK(cudaMemcpyAsync(&dt->total_iso, sl.iso_off.as<int64_t>() + np, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(&dt->total_units, sl.unit_off.as<int32_t>() + np, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(sl.h_totals, dt, sizeof(PlanTotals), cudaMemcpyDeviceToHost, st));
@@ -721,12 +732,17 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         int blocks = (int)std::min<int64_t>(((int64_t)n_units + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
         const bool pair = s->cfg.n_types == 2;
         size_t smem = wpb * sizeof(PsmSmem);
-        if (s->cfg.has_nl) {
-            if (pair) k_count_score<true, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
-            else k_count_score<true, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
-        } else {
-            if (pair) k_count_score<false, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
-            else k_count_score<false, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca);
+        // template switches: neutral losses configured, exactly two ion types, mz_error > 0.5
+        const int variant = (s->cfg.has_nl ? 4 : 0) | (pair ? 2 : 0) | (s->cfg.err_gt_half ? 1 : 0);
+        switch (variant) {
+            case 0: k_count_score<false, false, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            case 1: k_count_score<false, false, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            case 2: k_count_score<false, true, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            case 3: k_count_score<false, true, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            case 4: k_count_score<true, false, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            case 5: k_count_score<true, false, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            case 6: k_count_score<true, true, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            default: k_count_score<true, true, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
         }
         CK(cudaGetLastError());
         s->ctr.kernel_launches++; s->ctr.launches_count++;
@@ -766,6 +782,7 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.tie = sl.tie.as<unsigned long long>();
         sa.work_list = sl.work_list.as<int32_t>(); sa.work_count = sl.generic_count.as<int>() + 1;
         sa.work_cap = std::max<int64_t>(nm, 1);
+        sa.order = sl.order.as<int32_t>();
         const int wpb = 8;
         int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
         k_select<<<blocks, wpb * 32, wpb * PA_SORTCAP * sizeof(unsigned long long), st>>>(s->cfg, cs.b, sa);
