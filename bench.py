@@ -339,6 +339,14 @@ def main():
                "count_score": retained + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 12 * n_psm + 24 * int(ctr_dev["n_isoforms"]),
                "select": 4 * int(ctr_dev["n_isoforms"]) + 28 * n_psm + 20 * mod_total,
                "ascore": retained + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 16 * mod_total + 4 * mod_total}
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per PSM at
+        # 262144 PSMs/launch, profiles/traffic.json), scaled to this run's PSMs per launch
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj[args.workload][dom]["dram_bytes_per_psm"] * n_psm / max(n_launch, 1)
+        except Exception:
+            pass
         dom_ms = kern[dom] / max(n_launch, 1)
         achieved = alg[dom] / max(n_launch, 1) / (dom_ms * 1e-3) / 1e9
         step_alg = algorithmic_bytes(batch, mod_total)
@@ -356,7 +364,7 @@ def main():
                     "note": "bound by the host->device link: h2d_achieved_gbs vs a plain pinned 1 GiB copy on this box"},
             "gpu_launches": int(ctr_dev["kernel_launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "path is issue/latency bound, not HBM bound (DESIGN.md); frac is of the HBM copy peak",
                          "algorithmic_bytes_per_launch": alg[dom] / max(n_launch, 1), "launch_ms": dom_ms,
                          "step": {"algorithmic_bytes": step_alg, "kernel_ms": kernel_ms,

@@ -961,19 +961,15 @@ __device__ __forceinline__ void pa_depth_scores(const PaCfg& cfg, unsigned long 
     for (int d = 0; d < PA_N_TOP; d++) sc[d] = __ldg(cfg.T + pa_tab_index(n, pa_cum_get(lo, hi, d), d));
 }
 
-// append the warp's buffered Ascore entries (entry | class << 30) to the four global lists
-__device__ __forceinline__ void pa_flush_queue(const PaSelArgs& a, const uint32_t* s_queue, int qn) {
+// append the n buffered Ascore entries of class c to its global list (one atomic per flush)
+__device__ __forceinline__ void pa_flush_queue(const PaSelArgs& a, const int32_t* s_q, int c, int n) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    const uint32_t e = lane < qn ? s_queue[lane] : 0u;
-    for (int c = 0; c < 4; c++) {
-        const unsigned mask = __ballot_sync(PA_FULL, lane < qn && (int)(e >> 30) == c);
-        if (!mask) continue;
+    if (n > 0) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(a.work_count + c, __popc(mask));
+        if (lane == 0) base = atomicAdd(a.work_count + c, n);
         base = __shfl_sync(PA_FULL, base, 0);
-        if ((mask >> lane) & 1u)
-            a.work_list[(int64_t)c * a.work_cap + base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)(e & 0x3fffffffu);
+        if (lane < n) a.work_list[(int64_t)c * a.work_cap + base + lane] = s_q[lane];
     }
     __syncwarp();
 }
@@ -985,13 +981,17 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned long long* s_sort = (unsigned long long*)smem_raw + (size_t)wib * PA_SORTCAP;
-    __shared__ uint32_t s_queue_all[8][32];
-    uint32_t* s_queue = s_queue_all[wib];
-    int qn = 0;                                       // entries buffered by this warp (lane-uniform)
+    __shared__ int32_t s_queue_all[8][4][32];         // per warp and stream class: one k_ascore warp's worth
+    int32_t (*s_queue)[32] = s_queue_all[wib];
+    int qn0 = 0, qn1 = 0, qn2 = 0, qn3 = 0;           // entries buffered per class (lane-uniform)
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const float INF = __int_as_float(0x7f800000);
 
-    for (int64_t pi = gw; pi < a.n_psm; pi += nw) {
+    // every warp takes a contiguous run of the length-ordered PSMs, so the 32 entries it appends
+    // per flush -- one k_ascore warp -- stem from peptides of (nearly) the same length
+    const int64_t per = (a.n_psm + nw - 1) / nw;
+    const int64_t pi_end = (gw + 1) * per < a.n_psm ? (gw + 1) * per : a.n_psm;
+    for (int64_t pi = gw * per; pi < pi_end; pi++) {
         const int64_t p = a.order ? a.order[pi] : pi;
         const int status = a.psm_status[p];
         const int k = b.n_mod[p];
@@ -1100,17 +1100,23 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 // appended to the global lists 32 at a time (one atomic per class and flush).
                 const float wb = a.iso.w[ib + best];
                 if (!((double)fabsf(__fsub_rn(wb, m)) < 1e-6)) {
-                    if (qn == 32) { pa_flush_queue(a, s_queue, qn); qn = 0; }
                     const int Z = b.max_charge[p];
                     const int cls = cfg.has_nl ? 3 : (Z == 1 ? 0 : (Z == 2 ? 1 : (Z <= 4 ? 2 : 3)));
-                    if (lane == 0) s_queue[qn] = (uint32_t)(mo + j - a.mod_lo) | ((uint32_t)cls << 30);
+                    int& qn = cls == 0 ? qn0 : (cls == 1 ? qn1 : (cls == 2 ? qn2 : qn3));
+                    if (lane == 0) s_queue[cls][qn] = (int32_t)(mo + j - a.mod_lo);
                     qn++;
+                    // a full buffer is exactly one k_ascore warp: 32 entries of one class from
+                    // neighbouring PSMs of the length-ordered visit, i.e. merges of equal shape
+                    if (qn == 32) { pa_flush_queue(a, s_queue[cls], cls, 32); qn = 0; }
                 }
             }
         }
         __syncwarp();
     }
-    if (a.ascores) pa_flush_queue(a, s_queue, qn);
+    if (a.ascores) {
+        pa_flush_queue(a, s_queue[0], 0, qn0); pa_flush_queue(a, s_queue[1], 1, qn1);
+        pa_flush_queue(a, s_queue[2], 2, qn2); pa_flush_queue(a, s_queue[3], 3, qn3);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -277,3 +277,70 @@ def test_error_statuses():
         a.score(np.zeros(0), np.zeros(0), "PEPSTIDEK", 1)
     with pytest.raises(ValueError):
         PyAscore(100., 8, "STY", 79.966331)
+
+
+def _reverse_batch(batch):
+    """same PSMs and spectra in reversed order (different chunk cuts, different warp assignment)"""
+    n = batch["n_mod"].size
+    ns = batch["spec_off"].size - 1
+    sizes = np.diff(batch["spec_off"])[::-1]
+    so = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    src = np.repeat(batch["spec_off"][:-1][::-1], sizes) + (np.arange(so[-1]) - np.repeat(so[:-1], sizes))
+    pl = np.diff(batch["pep_off"])[::-1]
+    po = np.concatenate([[0], np.cumsum(pl)]).astype(np.int32)
+    psrc = np.repeat(batch["pep_off"][:-1][::-1], pl) + (np.arange(po[-1]) - np.repeat(po[:-1], pl))
+    al = np.diff(batch["aux_off"])[::-1]
+    ao = np.concatenate([[0], np.cumsum(al)]).astype(np.int32)
+    asrc = np.repeat(batch["aux_off"][:-1][::-1], al) + (np.arange(ao[-1]) - np.repeat(ao[:-1], al))
+    return dict(spec_off=so, mz=batch["mz"][src], inten=batch["inten"][src],
+                psm_spec=(ns - 1 - batch["psm_spec"][::-1]).astype(np.int32), pep_off=po, pep=batch["pep"][psrc],
+                n_mod=batch["n_mod"][::-1].copy(), max_charge=batch["max_charge"][::-1].copy(), aux_off=ao,
+                aux_pos=batch["aux_pos"][asrc.astype(np.int64)], aux_mass=batch["aux_mass"][asrc.astype(np.int64)])
+
+
+@pytest.mark.parametrize("workload,n", [("lowres_phospho", 200000), ("hires_phospho_nl", 100000), ("acetyl_k", 99999)])
+def test_large_batch_properties(workload, n):
+    """BASELINE-scale batches through size-independent properties: isoform counts from the binomial,
+    the reference's own invariants (test/test_ascore.py:63-97), independence of PSM order and chunk
+    cuts, and a random sample against the oracle"""
+    from math import comb
+    from pyascore_b200 import format_results
+    w = synth.WORKLOADS[workload]
+    meta = dict(scorer=w["scorer"], neutral_losses=w["neutral_losses"])
+    batch = synth.make_batch(workload, n, seed=31337, chunk_index=0)
+    s = make_scorer(meta)
+    res = s.score_batch(batch)
+    npsm = batch["n_mod"].size
+    assert np.all(res["psm_status"] == 0)
+    group = w["scorer"]["mod_group"].encode()
+    is_site = np.isin(batch["pep"], np.frombuffer(group, np.uint8))
+    S = np.add.reduceat(is_site.astype(np.int64), batch["pep_off"][:-1].astype(np.int64))
+    k = batch["n_mod"].astype(np.int64)
+    assert np.array_equal(res["n_sites"], S)
+    assert np.array_equal(res["n_iso"], np.array([comb(int(a), int(b)) for a, b in zip(S, k)]))
+    pop = np.array([bin(int(x)).count("1") for x in res["best_sig"]])
+    assert np.array_equal(pop, np.minimum(k, S))
+    sig_per_mod = np.repeat(res["best_sig"], k)
+    assert not np.any(res["alt_sites"] & sig_per_mod)                  # alternatives never sit on a chosen site
+    unamb = np.repeat(k >= S, k)
+    assert np.all(np.isinf(res["ascores"][unamb])) and np.all(res["alt_sites"][unamb] == 0)
+    assert np.all(np.isfinite(res["ascores"][~unamb])) and np.all(res["alt_sites"][~unamb] != 0)
+    assert np.all(res["best_score"] >= 0)
+    # reversed order: same results per PSM
+    r2 = s.score_batch(_reverse_batch(batch))
+    assert _golden.same_bits(r2["best_sig"][::-1], res["best_sig"]) and _golden.same_bits(r2["best_score"][::-1], res["best_score"])
+    mo = batch["mod_off"]
+    k_rev = k[::-1]
+    o2 = np.concatenate([[0], np.cumsum(k_rev)])
+    # entry j of PSM i sits at mo[i]+j in `res` and at o2[npsm-1-i]+j in `r2`
+    idx2 = np.repeat(o2[:-1][::-1], k) + (np.arange(mo[-1]) - np.repeat(mo[:-1], k))
+    assert _golden.same_bits(r2["ascores"][idx2], res["ascores"]) and _golden.same_bits(r2["alt_sites"][idx2], res["alt_sites"])
+    # a random sample against the oracle
+    rng = np.random.default_rng(3)
+    pick = np.sort(rng.choice(npsm, 400, replace=False))
+    ref = oracle_reference(meta, batch, pick)
+    for q, i in enumerate(pick):
+        seq, best, asc, alts = format_results(s, batch, res, i)
+        assert seq == ref["best_sequence"][q] and _golden.same_bits(np.float32(best), np.float32(ref["best_score"][q]))
+        assert _golden.same_bits(asc, ref["ascores"][q]) and all(_golden.same_bits(x, y) for x, y in zip(alts, ref["alts"][q]))
+    s.close()
