@@ -83,9 +83,14 @@ struct PaBinArgs {
 
 #define PA_NBIN_SMEM 128     // bins whose [start,end) ranges are tabulated in shared memory
 
-// shared memory per warp slot: mz f64[cap] (later {float mz, int bin}) | key u64[cap] |
-// bstart u16[128] | bend u16[128] | cell u8[256]
-#define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 16 + PA_NBIN_SMEM * 4 + PA_NCELL)
+// Shared memory per warp slot (cap = peaks per slot, a multiple of 32 and >= PA_BIN_MINCAP):
+//   [0, 16 cap)   staging: mz f64[cap] | intensity f64[cap]; the binning pass compacts it in place to
+//                 mzf f32[cap] at 0 and ranking keys (float)intensity f32[cap] at 8 cap (entry i lands in
+//                 the staging slot of entry i/2, which the pass has already consumed), after which
+//                 tie masks u32[128] sit at 4 cap and ranks u8[cap] at 4 cap + 512
+//   bin u8[cap] | bstart u16[128] | bend u16[128] | cell u8[256]
+#define PA_BIN_MINCAP 192
+#define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 17 + PA_NBIN_SMEM * 4 + PA_NCELL)
 
 __device__ __forceinline__ void pa_cp_async8(void* smem_dst, const void* gsrc) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -97,11 +102,14 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int cap = a.cap;
     unsigned char* slot = smem_raw + (size_t)wib * PA_BIN_SLOT_BYTES(cap);
-    double* s_mz = (double*)slot;
-    float2* s_mb = (float2*)slot;                 // after binning: {float mz, bin as int bits}, in place
-    float* s_out = (float*)slot;                  // retained (float)mz, compacted in place
-    uint64_t* s_key = (uint64_t*)(slot + (size_t)cap * 8);
-    uint16_t* s_bstart = (uint16_t*)(slot + (size_t)cap * 16);
+    double* s_mz = (double*)slot;                                    // staging
+    uint64_t* s_key = (uint64_t*)(slot + (size_t)cap * 8);           // staging (intensity bits)
+    float* s_mzf = (float*)slot;                                     // compacted (float)m/z, later the retained m/z
+    uint32_t* s_bmask = (uint32_t*)(slot + (size_t)cap * 4);         // per bin: ranks taken (bit r), bit 31 = tie seen
+    uint8_t* s_cnt = slot + (size_t)cap * 4 + PA_NBIN_SMEM * 4;      // rank of each peak inside its bin (255 = dropped)
+    float* s_hi = (float*)(slot + (size_t)cap * 8);                  // (float)intensity: the ranking key
+    uint8_t* s_bin = slot + (size_t)cap * 16;
+    uint16_t* s_bstart = (uint16_t*)(slot + (size_t)cap * 17);
     uint16_t* s_bend = s_bstart + PA_NBIN_SMEM;
     uint8_t* s_cell = (uint8_t*)(s_bend + PA_NBIN_SMEM);
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
@@ -114,7 +122,6 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
         if (P <= 0) { if (lane == 0) { a.rcount[s] = 0; a.chead[s] = make_float2(0.f, 0.f); } continue; }
         const bool fits = P <= cap;
         double mn, mx;
-        bool sorted = fits;
         if (fits) {
             // stage the whole spectrum with asynchronous 8-byte copies: every load of the warp is
             // in flight at once (the arrays are only 8-byte aligned at a CSR offset)
@@ -139,13 +146,16 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             if (n_bins < 1) n_bins = 1;     // degenerate spectrum: undefined in the reference
             dmin = (double)min_mz;
         };
-        bool tab = false;
+        bool fast = false;
         if (fits) {
             bounds();
-            tab = n_bins <= PA_NBIN_SMEM;
-            // bins, float m/z and intensity keys, in place; a sorted spectrum makes every bin one
-            // contiguous run [bstart, bend).  Sortedness is checked on what the fast path relies on:
+            fast = n_bins <= PA_NBIN_SMEM;
+        }
+        if (fast) {
+            // bins, float m/z and intensity keys; a sorted spectrum makes every bin one contiguous
+            // run [bstart, bend).  Sortedness is checked on what the fast path relies on:
             // non-decreasing bins and non-decreasing (float)m/z.
+            bool sorted = true;
             const double inv_bs = __ddiv_rn(1.0, dbs);
             int carry_bin = -1;
             float carry_mz = -INFINITY;
@@ -153,8 +163,13 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 const int i = base + lane;
                 int bq = 0x7fffffff;
                 float mzf = INFINITY;
+                float hi = 0.f;
                 if (i < P) {
                     const double m = s_mz[i];
+                    // ranking key: the intensity rounded to float.  The rounding is monotone, so two peaks
+                    // with different keys are ordered as their doubles are, and peaks of one bin that
+                    // share a key (ties, +-0, NaN) are caught below and ranked on the doubles instead
+                    hi = __double2float_rn(__longlong_as_double((long long)s_key[i]));
                     if (m < mn || m > mx) sorted = false;     // the ends must be the true extremes
                     const double x = __dsub_rn(m, dmin);
                     // floor(x / bin_size) as the reference computes it; the reciprocal product decides
@@ -168,84 +183,114 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                     if (b64 < 0) b64 = 0;           // only reachable for unsorted input (general path follows)
                     bq = (int)b64;
                     mzf = __double2float_rn(m);
-                    s_mb[i] = make_float2(mzf, __int_as_float(bq));   // own slot, in place
-                    s_key[i] = pa_inten_key(__longlong_as_double((long long)s_key[i]));
                 }
+                __syncwarp();                       // every lane has read its staging slots
+                if (i < P) { s_mzf[i] = mzf; s_hi[i] = hi; s_bin[i] = (uint8_t)bq; }
                 int bprev = __shfl_up_sync(PA_FULL, bq, 1);
                 float mprev = __shfl_up_sync(PA_FULL, mzf, 1);
                 if (lane == 0) { bprev = carry_bin; mprev = carry_mz; }
                 if (i < P) {
                     if (bq < bprev || mzf < mprev) sorted = false;
-                    if (tab) {
-                        if (bq != bprev) { s_bstart[bq] = (uint16_t)i; if (i > 0 && bprev >= 0 && bprev < PA_NBIN_SMEM) s_bend[bprev] = (uint16_t)i; }
-                        if (i == P - 1) s_bend[bq] = (uint16_t)P;
-                    }
+                    if (bq != bprev) { s_bstart[bq] = (uint16_t)i; if (i > 0 && bprev >= 0 && bprev < PA_NBIN_SMEM) s_bend[bprev] = (uint16_t)i; }
+                    if (i == P - 1) s_bend[bq] = (uint16_t)P;
                 }
                 carry_bin = __shfl_sync(PA_FULL, bq, 31);
                 carry_mz = __shfl_sync(PA_FULL, mzf, 31);
             }
-            sorted = __all_sync(PA_FULL, sorted);
+            fast = __all_sync(PA_FULL, sorted);
             __syncwarp();
         }
 
-        if (fits && sorted) {
-            int out = 0;
-            const uint2* s_k2 = (const uint2*)s_key;        // .y = high word of the intensity key
+        if (fast) {
+            // exact rank of peak i inside [b0, b1) from the full 64-bit intensity keys (read back from
+            // global memory: only needed when two peaks of a bin share a float key, or n_top > 31);
+            // an equal intensity wins only from an earlier index
+            auto exact_rank = [&](int i, int b0, int b1) {
+                const uint64_t ki = pa_inten_key(a.inten[off + i]);
+                int c = 0;
+                for (int j = b0; j < b1; j++) {
+                    const uint64_t kj = pa_inten_key(a.inten[off + j]);
+                    c += (kj > ki) || (kj == ki && j < i);
+                }
+                return c;
+            };
+            const bool exact_all = n_top > 31;
+            ((uint4*)s_bmask)[lane] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            // rank = peaks of the same bin that beat this one, counted on the float keys, four per
+            // shared-memory load; the first and last group of a bin are masked to [b0, b1).
+            // Two peaks of a bin with the same key get the same count: every kept peak marks its
+            // count in the bin's mask, and a mark found already set flags the bin for exact ranking.
+            const float4* h4 = (const float4*)s_hi;
             for (int base = 0; base < P; base += 32) {
                 const int i = base + lane;
-                int cnt = n_top, bq = 0;
+                if (i < P) {
+                    const int bq = s_bin[i];
+                    const int b0 = s_bstart[bq], b1 = s_bend[bq];
+                    int cnt;
+                    if (exact_all) cnt = exact_rank(i, b0, b1);
+                    else {
+                        const float hi = s_hi[i];
+                        const unsigned n = (unsigned)(b1 - b0);
+                        const int g0 = b0 >> 2, gl = (b1 - 1) >> 2;
+                        const float NINF = __int_as_float(0xff800000);
+                        float4 v = h4[g0];
+                        int r = (g0 << 2) - b0;
+                        v.x = (unsigned)r < n ? v.x : NINF; v.y = (unsigned)(r + 1) < n ? v.y : NINF;
+                        v.z = (unsigned)(r + 2) < n ? v.z : NINF; v.w = (unsigned)(r + 3) < n ? v.w : NINF;
+                        // one compare-to-1.0f and one add per peak; the sums are small integers, exact in float
+                        float c = (v.x > hi ? 1.f : 0.f) + (v.y > hi ? 1.f : 0.f) + (v.z > hi ? 1.f : 0.f) + (v.w > hi ? 1.f : 0.f);
+                        for (int g = g0 + 1; g < gl; g++) {
+                            v = h4[g];
+                            c += (v.x > hi ? 1.f : 0.f) + (v.y > hi ? 1.f : 0.f) + (v.z > hi ? 1.f : 0.f) + (v.w > hi ? 1.f : 0.f);
+                        }
+                        if (gl > g0) {
+                            v = h4[gl];
+                            r = (gl << 2) - b0;
+                            v.x = (unsigned)r < n ? v.x : NINF; v.y = (unsigned)(r + 1) < n ? v.y : NINF;
+                            v.z = (unsigned)(r + 2) < n ? v.z : NINF; v.w = (unsigned)(r + 3) < n ? v.w : NINF;
+                            c += (v.x > hi ? 1.f : 0.f) + (v.y > hi ? 1.f : 0.f) + (v.z > hi ? 1.f : 0.f) + (v.w > hi ? 1.f : 0.f);
+                        }
+                        cnt = (int)c;
+                        if (cnt < n_top) {
+                            const uint32_t bit = 1u << cnt;
+                            if (atomicOr(&s_bmask[bq], bit) & bit) atomicOr(&s_bmask[bq], 0x80000000u);
+                        }
+                    }
+                    s_cnt[i] = (uint8_t)(cnt < n_top ? cnt : 255);
+                }
+            }
+            __syncwarp();
+            int out = 0;
+            for (int base = 0; base < P; base += 32) {
+                const int i = base + lane;
+                int cnt = 255, bq = 0;
                 float mzf = 0.f;
                 if (i < P) {
-                    const float2 mb = s_mb[i];
-                    mzf = mb.x;
-                    bq = __float_as_int(mb.y);
-                    const uint64_t ki = s_key[i];
-                    cnt = 0;
-                    if (tab) {
-                        // rank = peaks of the same bin that beat this one.  The high words of the
-                        // keys decide unless another peak of the bin shares this one's high word;
-                        // then the full keys are compared, an equal intensity winning only from an
-                        // earlier index: (kj + [j < i]) > ki covers both sides of i
-                        const int b0 = s_bstart[bq], b1 = s_bend[bq];
-                        const uint32_t hi = (uint32_t)(ki >> 32);
-                        int eq = 0, j = b0;
-                        for (; j + 4 <= b1; j += 4) {
-                            const uint32_t h0 = s_k2[j].y, h1 = s_k2[j + 1].y, h2 = s_k2[j + 2].y, h3 = s_k2[j + 3].y;
-                            cnt += (h0 > hi) + (h1 > hi) + (h2 > hi) + (h3 > hi);
-                            eq += (h0 == hi) + (h1 == hi) + (h2 == hi) + (h3 == hi);
-                        }
-                        for (; j < b1; j++) {
-                            const uint32_t h = s_k2[j].y;
-                            cnt += (h > hi);
-                            eq += (h == hi);
-                        }
-                        if (eq > 1) {
-                            cnt = 0;
-                            for (int j = b0; j < b1; j++) cnt += ((s_key[j] + (uint64_t)(j < i)) > ki);
-                        }
-                    } else {
-                        for (int j = i - 1; j >= 0 && cnt < n_top && __float_as_int(s_mb[j].y) == bq; j--) cnt += (s_key[j] >= ki);
-                        for (int j = i + 1; j < P && cnt < n_top && __float_as_int(s_mb[j].y) == bq; j++) cnt += (s_key[j] > ki);
-                    }
+                    mzf = s_mzf[i];
+                    bq = s_bin[i];
+                    cnt = s_cnt[i];
+                    if (!exact_all && (s_bmask[bq] >> 31)) cnt = exact_rank(i, s_bstart[bq], s_bend[bq]);
                 }
                 const bool keep = cnt < n_top;
-                unsigned bal = __ballot_sync(PA_FULL, keep);   // every lane has read its own s_mb slot by now
+                unsigned bal = __ballot_sync(PA_FULL, keep);   // every lane has read its own s_mzf entry by now
                 if (keep) {
                     int pos = out + __popc(bal & ((1u << lane) - 1u));
                     a.rmz[off + pos] = mzf;
                     a.rrank[off + pos] = (uint8_t)cnt;
                     if (a.rindex) { a.rindex[off + pos] = i; a.rbin[off + pos] = bq; }
-                    if (tab) s_out[pos] = mzf;      // pos <= i: only slots this or earlier chunks own
+                    s_mzf[pos] = mzf;               // pos <= i: only entries this or earlier chunks own
                 }
                 out += __popc(bal);
                 __syncwarp();
             }
+            const float* s_out = s_mzf;
             if (lane == 0) {
                 a.rcount[s] = out;
                 if (a.bounds) { a.bounds[3 * s] = min_mz; a.bounds[3 * s + 1] = max_mz; a.bounds[3 * s + 2] = (float)n_bins; }
             }
             // m/z cell index over the retained peaks (consumers: pa_match_rank)
-            if (tab && out <= PA_RCAP && out > 0) {
+            if (out <= PA_RCAP && out > 0) {
                 __syncwarp();
                 const float cbase = s_out[0];
                 const float cinv = pa_cell_inv(cbase, s_out[out - 1]);
@@ -439,6 +484,7 @@ struct PaCountArgs {
     const int32_t* psm_status;
     PaIso iso;
     unsigned long long* n_lookups;   // counter
+    unsigned long long* next_unit;   // work cursor (zeroed before the launch): warps grab PA_K2_GRAB units at a time
 };
 
 #ifndef PA_K2_MINBLOCKS
@@ -446,6 +492,9 @@ struct PaCountArgs {
 #endif
 #ifndef PA_K2_UNROLL
 #define PA_K2_UNROLL 1
+#endif
+#ifndef PA_K2_GRAB
+#define PA_K2_GRAB 4
 #endif
 // One fragment position: every neutral-loss variant and charge of running sum `run`, matched
 // against the staged peaks; adds the packed per-rank increments (`lut[r]`, lut[10] = 0 for "no
@@ -583,7 +632,17 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
     PsmInfo info;
     unsigned long long lookups = 0;
     const int T = PAIR ? 2 : 1;
-    for (int64_t u = gw; u < a.n_units; u += nw) {
+    // Units differ in cost by two orders of magnitude (1 .. 1024 isoforms), so they are handed out
+    // dynamically: a warp takes PA_K2_GRAB consecutive units from a global cursor and asks for its next
+    // grab before it starts on the current one (the atomic's round trip hides behind the work).
+    (void)gw; (void)nw;
+    unsigned long long pend = 0;
+    if (lane == 0) pend = atomicAdd(a.next_unit, (unsigned long long)PA_K2_GRAB);
+    int64_t base = (int64_t)__shfl_sync(PA_FULL, pend, 0);
+    while (base < a.n_units) {
+      if (lane == 0) pend = atomicAdd(a.next_unit, (unsigned long long)PA_K2_GRAB);
+      const int64_t u_end = base + PA_K2_GRAB < a.n_units ? base + PA_K2_GRAB : a.n_units;
+      for (int64_t u = base; u < u_end; u++) {
         const int64_t p = a.unit_psm[u];
         const int64_t I = a.iso_off[p + 1] - a.iso_off[p];
         if (p != cur) { pa_setup_psm(cfg, b, p, sm, info, true); cur = p; }
@@ -629,6 +688,8 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
                 a.iso.w[g] = pa_weighted(cfg, clo, chi, (int)nf);
             }
         }
+      }
+      base = (int64_t)__shfl_sync(PA_FULL, pend, 0);
     }
     for (int o = 16; o > 0; o >>= 1) lookups += __shfl_xor_sync(PA_FULL, lookups, o);
     if (lane == 0 && lookups) atomicAdd(a.n_lookups, lookups);
@@ -678,7 +739,12 @@ struct PaSelArgs {
     int* work_count;             // [4]              by stream class (k_ascore)
     int64_t work_cap;
     const int32_t* order;        // [n_psm] PSMs by peptide length: neighbouring Ascore entries then run
-};                               //         merges of similar length, which keeps k_ascore's warps converged
+                                 //         merges of similar length, which keeps k_ascore's warps converged
+    unsigned long long* next_psm;    // work cursor into `order` (zeroed before the launch)
+};
+#ifndef PA_SEL_GRAB
+#define PA_SEL_GRAB 16
+#endif
 
 // --- libstdc++ std::sort (introsort + final insertion sort), comparator a.w > b.w ------------
 // bits/stl_algo.h of GCC 13, as in SURVEY.md appendix A.2.  Elements are (float w, uint32 id)
@@ -987,11 +1053,18 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const float INF = __int_as_float(0x7f800000);
 
-    // every warp takes a contiguous run of the length-ordered PSMs, so the 32 entries it appends
-    // per flush -- one k_ascore warp -- stem from peptides of (nearly) the same length
-    const int64_t per = (a.n_psm + nw - 1) / nw;
-    const int64_t pi_end = (gw + 1) * per < a.n_psm ? (gw + 1) * per : a.n_psm;
-    for (int64_t pi = gw * per; pi < pi_end; pi++) {
+    // Warps take runs of PA_SEL_GRAB consecutive PSMs of the length-ordered list from a global cursor
+    // (the cost per PSM grows with its isoform count, so a static split leaves warps idle).  All warps
+    // advance through the list together, so the 32 entries a warp appends per flush -- one k_ascore
+    // warp -- still stem from peptides of (nearly) the same length.
+    (void)gw; (void)nw;
+    unsigned long long pend = 0;
+    if (lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)PA_SEL_GRAB);
+    int64_t run0 = (int64_t)__shfl_sync(PA_FULL, pend, 0);
+    while (run0 < a.n_psm) {
+      if (lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)PA_SEL_GRAB);
+      const int64_t pi_end = run0 + PA_SEL_GRAB < a.n_psm ? run0 + PA_SEL_GRAB : a.n_psm;
+      for (int64_t pi = run0; pi < pi_end; pi++) {
         const int64_t p = a.order ? a.order[pi] : pi;
         const int status = a.psm_status[p];
         const int k = b.n_mod[p];
@@ -1112,6 +1185,8 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
             }
         }
         __syncwarp();
+      }
+      run0 = (int64_t)__shfl_sync(PA_FULL, pend, 0);
     }
     if (a.ascores) {
         pa_flush_queue(a, s_queue[0], 0, qn0); pa_flush_queue(a, s_queue[1], 1, qn1);

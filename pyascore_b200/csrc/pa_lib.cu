@@ -60,7 +60,7 @@ struct Slot {                // per-stream working set
     // plan
     DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp, sort_key, sort_idx, sort_key2, order;
     // K2/K3
-    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, best_idx, mod_psm, tie, generic_list, generic_count, work_list;
+    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, sched, best_idx, mod_psm, tie, generic_list, generic_count, work_list;
     // staged outputs
     DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
     PlanTotals* h_totals = nullptr;      // pinned
@@ -70,7 +70,7 @@ struct Slot {                // per-stream working set
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &sort_key, &sort_idx, &sort_key2, &order, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lists, &lookups, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_list, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_list, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_totals) cudaFreeHost(h_totals);
@@ -121,6 +121,35 @@ struct pa_scorer {
     int attr_set = 0;
     bool binner_only = false;
 };
+
+// Blocks of `kernel` one SM keeps resident at this block size and dynamic shared memory: the
+// persistent kernels launch exactly one such wave (sm_count * resident_blocks) and loop.
+template <typename K>
+static int resident_blocks(K kernel, int threads, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = 1;
+    }
+    return n;
+}
+
+// Launch shape of k_bin_topn for spectra of up to `max_peaks` peaks: slot capacity, warps per block
+// (the count that keeps the most warps resident per SM -- the slots are what limits occupancy) and a
+// grid of one resident wave.
+static void bin_launch_shape(int sm_count, int64_t max_peaks, int64_t n_spec, int* cap_out, int* wpb_out,
+                             size_t* smem_out, int* blocks_out) {
+    int cap = (int)std::min<int64_t>(((std::max<int64_t>(max_peaks, PA_BIN_MINCAP) + 31) / 32) * 32, 4096);
+    int best_wpb = 1, best_warps = 0, best_res = 1;
+    for (int wpb = 8; wpb >= 1; wpb--) {
+        const size_t smem = (size_t)wpb * PA_BIN_SLOT_BYTES(cap);
+        if (smem > 200 * 1024) continue;
+        const int res = resident_blocks(k_bin_topn, wpb * 32, smem);
+        if (res * wpb > best_warps) { best_warps = res * wpb; best_wpb = wpb; best_res = res; }
+    }
+    *cap_out = cap; *wpb_out = best_wpb; *smem_out = (size_t)best_wpb * PA_BIN_SLOT_BYTES(cap);
+    *blocks_out = (int)std::max<int64_t>(1, std::min<int64_t>((n_spec + best_wpb - 1) / best_wpb, (int64_t)sm_count * best_res));
+}
 
 static int fail(pa_scorer* s, int code, const char* fmt, ...) {
     char buf[1024];
@@ -623,12 +652,11 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     ba.ctab = sl.ctab.as<uint8_t>(); ba.chead = sl.chead.as<float2>();
     ba.bin_size = s->bin_size; ba.n_top = s->n_top;
     ba.rindex = nullptr; ba.rbin = nullptr; ba.bounds = nullptr;
-    int cap = ((std::max(max_peaks, 32) + 31) / 32) * 32;
-    cap = std::min(cap, 4096);
-    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / (int64_t)PA_BIN_SLOT_BYTES(cap)));
+    // one resident wave: the grid-stride loop gives every warp the same number of spectra
+    int cap, wpb, blocks;
+    size_t smem;
+    bin_launch_shape(s->sm_count, max_peaks, ns, &cap, &wpb, &smem, &blocks);
     ba.cap = cap;
-    size_t smem = (size_t)wpb * PA_BIN_SLOT_BYTES(cap);
-    int blocks = (int)std::min<int64_t>((ns + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
     cs.e_bin0 = next_event(s); cs.e_bin1 = next_event(s); cs.e_plan1 = next_event(s);
     CK(cudaEventRecord(cs.e_bin0, st));
     if (ns > 0) {
@@ -717,6 +745,8 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     iso.lo = sl.iso_lo.as<unsigned long long>(); iso.hi = sl.iso_hi.as<unsigned long long>();
     iso.nfrag = sl.iso_n.as<uint32_t>(); iso.w = sl.iso_w.as<float>();
     cs.e_cnt0 = next_event(s); cs.e_cnt1 = next_event(s); cs.e_sel1 = next_event(s);
+    CK(sl.sched.ensure(16));                          // work cursors of k_count_score [0] and k_select [1]
+    CK(cudaMemsetAsync(sl.sched.p, 0, 16, st));
     if (np > 0) {
         k_expand_units<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(np, sl.unit_off.as<int32_t>(), sl.unit_psm.as<int32_t>());
         CK(cudaGetLastError());
@@ -729,21 +759,27 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         ca.iso_off = sl.iso_off.as<int64_t>(); ca.psm_S = sl.psm_S.as<int32_t>(); ca.psm_status = sl.psm_status.as<int32_t>();
         ca.iso = iso; ca.n_lookups = sl.lookups.as<unsigned long long>();
         const int wpb = 8;
-        int blocks = (int)std::min<int64_t>(((int64_t)n_units + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
         const bool pair = s->cfg.n_types == 2;
         size_t smem = wpb * sizeof(PsmSmem);
-        // template switches: neutral losses configured, exactly two ion types, mz_error > 0.5
+        ca.next_unit = sl.sched.as<unsigned long long>();
+        const int64_t want = ((int64_t)n_units + wpb - 1) / wpb;
+        // template switches: neutral losses configured, exactly two ion types, mz_error > 0.5.
+        // One resident wave of blocks; the warps pull units from the cursor.
+#define PA_K2_LAUNCH(NL, PR, EG) { \
+            int blocks = (int)std::min<int64_t>(want, (int64_t)s->sm_count * resident_blocks(k_count_score<NL, PR, EG>, wpb * 32, smem)); \
+            k_count_score<NL, PR, EG><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); }
         const int variant = (s->cfg.has_nl ? 4 : 0) | (pair ? 2 : 0) | (s->cfg.err_gt_half ? 1 : 0);
         switch (variant) {
-            case 0: k_count_score<false, false, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
-            case 1: k_count_score<false, false, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
-            case 2: k_count_score<false, true, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
-            case 3: k_count_score<false, true, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
-            case 4: k_count_score<true, false, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
-            case 5: k_count_score<true, false, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
-            case 6: k_count_score<true, true, false><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
-            default: k_count_score<true, true, true><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); break;
+            case 0: PA_K2_LAUNCH(false, false, false) break;
+            case 1: PA_K2_LAUNCH(false, false, true) break;
+            case 2: PA_K2_LAUNCH(false, true, false) break;
+            case 3: PA_K2_LAUNCH(false, true, true) break;
+            case 4: PA_K2_LAUNCH(true, false, false) break;
+            case 5: PA_K2_LAUNCH(true, false, true) break;
+            case 6: PA_K2_LAUNCH(true, true, false) break;
+            default: PA_K2_LAUNCH(true, true, true) break;
         }
+#undef PA_K2_LAUNCH
         CK(cudaGetLastError());
         s->ctr.kernel_launches++; s->ctr.launches_count++;
     }
@@ -783,9 +819,11 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.work_list = sl.work_list.as<int32_t>(); sa.work_count = sl.generic_count.as<int>() + 1;
         sa.work_cap = std::max<int64_t>(nm, 1);
         sa.order = sl.order.as<int32_t>();
+        sa.next_psm = sl.sched.as<unsigned long long>() + 1;
         const int wpb = 8;
-        int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
-        k_select<<<blocks, wpb * 32, wpb * PA_SORTCAP * sizeof(unsigned long long), st>>>(s->cfg, cs.b, sa);
+        const size_t sel_smem = wpb * PA_SORTCAP * sizeof(unsigned long long);
+        int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * resident_blocks(k_select, wpb * 32, sel_smem));
+        k_select<<<blocks, wpb * 32, sel_smem, st>>>(s->cfg, cs.b, sa);
         CK(cudaGetLastError());
         s->ctr.kernel_launches++; s->ctr.launches_select++;
     }
@@ -1102,11 +1140,11 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     ba.rindex = extra ? d_index.as<int32_t>() - lo : nullptr;
     ba.rbin = extra ? d_bin.as<int32_t>() - lo : nullptr;
     ba.bounds = extra ? d_bounds.as<float>() : nullptr;
-    int cap = (int)std::min<int64_t>(((std::max<int64_t>(m, 32) + 31) / 32) * 32, 4096);
-    int wpb = (int)std::min<int64_t>(8, std::max<int64_t>(1, (100 * 1024) / (int64_t)PA_BIN_SLOT_BYTES(cap)));
+    int cap, wpb, blocks;
+    size_t smem;
+    bin_launch_shape(s->sm_count, m, n_spec, &cap, &wpb, &smem, &blocks);
     ba.cap = cap;
-    int blocks = (int)std::min<int64_t>((n_spec + wpb - 1) / wpb, (int64_t)s->sm_count * 8);
-    k_bin_topn<<<blocks, wpb * 32, (size_t)wpb * PA_BIN_SLOT_BYTES(cap), st>>>(ba);
+    k_bin_topn<<<blocks, wpb * 32, smem, st>>>(ba);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_mz + lo, sl.rmz.p, (size_t)npk * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_rank + lo, sl.rrank.p, (size_t)npk, cudaMemcpyDeviceToHost, st));

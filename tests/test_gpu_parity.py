@@ -171,6 +171,20 @@ def test_binning_matches_oracle(bin_size):
         specs.append((rng.uniform(100., 2000., n), rng.lognormal(5., 1., n)))
     # exact multiples of 100 at both ends
     specs.append((np.array([100., 150., 250.5, 300.]), np.array([4., 3., 2., 1.])))
+    # intensities that are distinct as doubles but collide once rounded to float (K1 ranks on float keys
+    # and must fall back to the doubles for exactly these bins), alone and mixed with ordinary peaks
+    for n in [40, 300, 1000]:
+        mz = np.sort(rng.uniform(100., 2000., n))
+        near = 5000. + rng.permutation(n) * 1e-7
+        specs.append((mz, near))
+        mixed = rng.lognormal(5., 1., n)
+        pick = rng.random(n) < 0.3
+        mixed[pick] = 321.5 + rng.permutation(n)[pick] * 1e-9
+        specs.append((mz, mixed))
+    # negative, tiny and huge intensities (beyond the float range: keys saturate to +-inf / flush towards 0)
+    mz = np.sort(rng.uniform(100., 2000., 400))
+    wild = rng.standard_normal(400) * 10. ** rng.integers(-60, 60, 400)
+    specs.append((mz, wild))
     off = np.zeros(len(specs) + 1, np.int64)
     np.cumsum([m.size for m, _ in specs], out=off[1:])
     omz, ork, ocnt = s.bin_spectra(off, np.concatenate([m for m, _ in specs]), np.concatenate([i for _, i in specs]))

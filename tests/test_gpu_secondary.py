@@ -18,6 +18,28 @@ def u32(x):
     return np.array(x, dtype=np.uint32)
 
 
+@pytest.mark.parametrize("n_top,bin_size", [(40, 100.), (3, 25.), (254, 1000.), (12, 2.5)])
+def test_binned_spectra_other_depths_vs_oracle(n_top, bin_size):
+    """n_top beyond the scoring depth (exact-rank path of K1 for n_top > 31) and bin counts beyond the
+    shared-memory tables (general path), sorted input"""
+    from oracle.cscorer import OraclePyAscore
+    from pyascore_b200 import PyBinnedSpectra
+    rng = np.random.default_rng(77)
+    masses = np.sort(rng.uniform(300., 1800., 1200))
+    intens = rng.lognormal(5., 1., 1200)
+    spec = PyBinnedSpectra(bin_size=bin_size, n_top=n_top)
+    spec.consume_spectra(masses, intens)
+    ob = OraclePyAscore(bin_size, n_top, "STY", PH).binned(masses, intens)
+    k = 0
+    for b in range(spec.n_bins):
+        spec.bin = b
+        for r in range(spec.n_peaks):
+            spec.rank = r
+            assert (ob["bin"][k], ob["rank"][k], ob["mz"][k], ob["intensity"][k]) == (b, r, spec.mz, spec.intensity)
+            k += 1
+    assert k == ob["mz"].size
+
+
 # ---------------------------------------------------------------------------------------------
 def test_binned_spectra_toy():
     """test/test_spectra_container.py:15-35"""
