@@ -342,9 +342,22 @@ def main():
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per PSM at
         # 262144 PSMs/launch, profiles/traffic.json), scaled to this run's PSMs per launch
         traffic = None
+        issue = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tj[args.workload][dom]["dram_bytes_per_psm"] * n_psm / max(n_launch, 1)
+            # issue-slot view of the same kernel (the path is bound by warp-instruction issue):
+            # executed warp instructions per PSM from the committed ncu capture x PSMs per launch / the launch
+            # time measured here, against SMs x 4 schedulers x the SM clock sampled during this run
+            props = torch.cuda.get_device_properties(local)
+            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+            ipeak = props.multi_processor_count * 4 * mhz * 1e6
+            iach = tj[args.workload][dom]["warp_inst_per_psm"] * n_psm / (kern[dom] * 1e-3)
+            all_inst = sum(tj[args.workload][k]["warp_inst_per_psm"] for k in ("bin_topn", "count_score", "select", "ascore"))
+            issue = {"achieved": iach, "peak": ipeak, "unit": "warp-inst/s", "frac": iach / ipeak,
+                     "warp_inst_per_psm": tj[args.workload][dom]["warp_inst_per_psm"],
+                     "step_frac": all_inst * n_psm / (sum(kern[k] for k in ("bin_topn", "count_score", "select", "ascore")) * 1e-3) / ipeak,
+                     "source": "profiles/traffic.json (ncu smsp__inst_executed.sum) x this run's CUDA-event times"}
         except Exception:
             pass
         dom_ms = kern[dom] / max(n_launch, 1)
@@ -367,6 +380,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "path is issue/latency bound, not HBM bound (DESIGN.md); frac is of the HBM copy peak",
                          "algorithmic_bytes_per_launch": alg[dom] / max(n_launch, 1), "launch_ms": dom_ms,
+                         "issue": issue,
                          "step": {"algorithmic_bytes": step_alg, "kernel_ms": kernel_ms,
                                   "achieved": step_alg / (kernel_ms * 1e-3) / 1e9,
                                   "frac": step_alg / (kernel_ms * 1e-3) / 1e9 / peak}},

@@ -1282,11 +1282,19 @@ struct AscPeaks {
     const float* pm; const uint8_t* pr; int R; const uint8_t* ctab; float cbase, cinv;
 };
 
+#define ASC_BLOCK 128
+
+// a survivor of the merge: one trial of its list, a hit when its matched peak is ranked within `depth`
+__device__ __forceinline__ void asc_survivor(const PaCfg& cfg, const AscPeaks& pk, int depth, float v, bool from_a,
+                                             int& hitsA, int& trialsA, int& hitsB, int& trialsB) {
+    const int hit = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, v, cfg.err, cfg.err_gt_half) <= depth;
+    if (from_a) { trialsA++; hitsA += hit; } else { trialsB++; hitsB += hit; }
+}
+
 // ---- general stream form (neutral losses and/or more than four charges) ---------------------
 // Per thread up to PA_MAXSTREAM streams per list, one per (neutral-loss sum, charge); their state
 // lives in shared memory ([field][list][stream][thread]: conflict-free) so that a stream can be
 // addressed by a run-time index without spilling to local memory.
-#define ASC_BLOCK 128
 struct AscSm {
     float run[2][PA_MAXSTREAM][ASC_BLOCK];     // float32 running sum at the stream's current step
     float val[2][PA_MAXSTREAM][ASC_BLOCK];     // pending fragment m/z (+inf: exhausted)
@@ -1357,8 +1365,8 @@ __device__ __forceinline__ int asc_streams_init(const PaCfg& cfg, const AscPep& 
 
 __device__ __forceinline__ bool asc_merge_streams(const PaCfg& cfg, const AscPep& q, const AscPeaks& pk, bool fwd,
                                                   double a1, double a2, uint64_t alo, uint64_t ahi, uint64_t blo,
-                                                  uint64_t bhi, int depth, int& hitsA, int& trialsA, int& hitsB,
-                                                  int& trialsB) {
+                                                  uint64_t bhi, int depth, int& hitsA, int& trialsA,
+                                                  int& hitsB, int& trialsB) {
     extern __shared__ __align__(16) unsigned char asc_smem_raw[];
     AscSm* sm = (AscSm*)asc_smem_raw;
     const int tid = threadIdx.x;
@@ -1405,9 +1413,8 @@ __device__ __forceinline__ bool asc_merge_streams(const PaCfg& cfg, const AscPep
             else takeA = x < y;
             if (takeA < 0) { hx = false; hy = false; }
             else {
-                const int hit = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, takeA ? x : y, cfg.err, cfg.err_gt_half) <= depth;
-                if (takeA) { trialsA++; hitsA += hit; hx = false; }
-                else { trialsB++; hitsB += hit; hy = false; }
+                asc_survivor(cfg, pk, depth, takeA ? x : y, takeA != 0, hitsA, trialsA, hitsB, trialsB);
+                if (takeA) hx = false; else hy = false;
             }
         }
     }
@@ -1416,9 +1423,15 @@ __device__ __forceinline__ bool asc_merge_streams(const PaCfg& cfg, const AscPep
 
 // greedy tolerance merge of cpp/ModifiedPeptide.cpp:288-316 over the streams of the best isoform
 // (mask a) and one competitor (mask b) for one ion type; false = needs the generic kernel.
-// The loop is written as a small state machine -- at most one pop per trip, taken from whichever
-// list lacks a head, then one decision when both heads are settled -- so that the lanes of a
-// warp, which sit at different points of different merges, still execute the same instructions.
+//
+// Two exact shortcuts keep the merge short:
+//  * Common prefix.  Up to the first residue at which the two isoforms differ (step d of the walk)
+//    both lists hold the same fragments.  With T = the smallest fragment of step d over both lists and
+//    all charges, every fragment below T stems from a common step, so the sorted lists start with the
+//    same values and the greedy merge drops them pairwise (|x - y| = 0 < mz_error).  The streams are
+//    therefore started at their first fragment >= T; the steps before cost one float add each.
+//  * One trip settles both heads.  A trip pops a head for whichever list lacks one (both, after a
+//    pairwise drop) and then takes the one decision the reference takes on two settled heads.
 template <int NQ>
 __device__ __forceinline__ bool asc_merge_type(const PaCfg& cfg, const AscPep& q, const AscPeaks& pk, char type,
                                                uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi, int depth,
@@ -1435,64 +1448,118 @@ __device__ __forceinline__ bool asc_merge_type(const PaCfg& cfg, const AscPep& q
         const float PINF = __int_as_float(0x7f800000);
         float runA[NQ], valA[NQ], runB[NQ], valB[NQ];
         int stepA[NQ], stepB[NQ];
-        {
-            const int i = fwd ? 0 : L - 1;
+        auto res_at = [&](int step, uint64_t mlo, uint64_t mhi) {
+            const int i = fwd ? step : L - 1 - step;
             int idx;
-            const float rA = asc_res(cfg, q, i, (int)(((i < 64) ? (alo >> i) : (ahi >> (i - 64))) & 1ull), idx);
-            const float rB = asc_res(cfg, q, i, (int)(((i < 64) ? (blo >> i) : (bhi >> (i - 64))) & 1ull), idx);
-            const double dA = __dsub_rn(__dadd_rn((double)rA, a1), a2), dB = __dsub_rn(__dadd_rn((double)rB, a1), a2);
+            return asc_res(cfg, q, i, (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull), idx);
+        };
+        auto frag = [&](float run, int z) { return pa_charge_mz(__dsub_rn(__dadd_rn((double)run, a1), a2), z); };
+        // d = first step whose residue differs between the two isoforms
+        int d;
+        {
+            const uint64_t xlo = alo ^ blo, xhi = ahi ^ bhi;
+            const int p_first = xlo ? __ffsll((long long)xlo) - 1 : (xhi ? 63 + __ffsll((long long)xhi) : 128);
+            const int p_last = xhi ? 127 - __clzll((long long)xhi) : (xlo ? 63 - __clzll((long long)xlo) : -1);
+            d = fwd ? p_first : L - 1 - p_last;
+            if (!(cfg.err > 0.f)) d = 0;                 // nothing is ever dropped: no shortcut
+            d = d < 0 ? 0 : (d > steps ? steps : d);
+        }
+        // float32 running sum over the common steps [0, d)
+        float runc = 0.f;
+        for (int s = 0; s < d; s++) {
+            const float r = res_at(s, alo, ahi);
+            const float nr = (s == 0) ? r : __fadd_rn(r, runc);
+            if (s > 0 && nr < runc) mono = false;
+            runc = nr;
+        }
+        if (d >= steps) return mono;                     // every walked residue is common: all fragments drop
+        float runAd = res_at(d, alo, ahi), runBd = res_at(d, blo, bhi);
+        if (d > 0) {
+            runAd = __fadd_rn(runAd, runc); runBd = __fadd_rn(runBd, runc);
+            if (runAd < runc || runBd < runc) mono = false;
+        }
+        float T = PINF;
 #pragma unroll
-            for (int z = 0; z < NQ; z++) {
-                runA[z] = rA; runB[z] = rB; stepA[z] = 0; stepB[z] = 0;
-                valA[z] = (z < Z) ? pa_charge_mz(dA, z + 1) : PINF;
-                valB[z] = (z < Z) ? pa_charge_mz(dB, z + 1) : PINF;
+        for (int z = 0; z < NQ; z++)
+            if (z < Z) { const float va = frag(runAd, z + 1), vb = frag(runBd, z + 1); T = fminf(T, fminf(va, vb)); }
+#pragma unroll
+        for (int z = 0; z < NQ; z++) {
+            runA[z] = runAd; runB[z] = runBd; stepA[z] = d; stepB[z] = d;
+            valA[z] = (z < Z) ? frag(runAd, z + 1) : PINF;
+            valB[z] = (z < Z) ? frag(runBd, z + 1) : PINF;
+        }
+        if (NQ > 1 && d > 0 && Z > 1) {
+            // a lower charge reaches T at an earlier (common) step: start its streams there
+            unsigned open = (1u << Z) - 1u;              // streams not yet started
+            float run = 0.f;
+            for (int s = 0; s < d && open; s++) {
+                const float r = res_at(s, alo, ahi);
+                run = (s == 0) ? r : __fadd_rn(r, run);
+#pragma unroll
+                for (int z = 0; z < NQ; z++) {
+                    if ((open >> z) & 1u) {
+                        const float v = frag(run, z + 1);
+                        if (v >= T) {
+                            runA[z] = run; runB[z] = run; stepA[z] = s; stepB[z] = s; valA[z] = v; valB[z] = v;
+                            open &= ~(1u << z);
+                        }
+                    }
+                }
             }
         }
-        int leftA = Z * steps, leftB = Z * steps;
-        for (;;) {
-            const bool needA = !hx && leftA > 0, needB = !hy && leftB > 0;
-            if (needA || needB) {
-                const bool w = !needA;                           // pop from B only when A has its head
-                int bq = 0;
-                float xm = w ? valB[0] : valA[0], runb = w ? runB[0] : runA[0];
-                int stepb = w ? stepB[0] : stepA[0];
+        int leftA = 0;
 #pragma unroll
-                for (int i = 1; i < NQ; i++) {
-                    const float v = w ? valB[i] : valA[i];
-                    if (v < xm) { xm = v; bq = i; runb = w ? runB[i] : runA[i]; stepb = w ? stepB[i] : stepA[i]; }
-                }
+        for (int z = 0; z < NQ; z++) if (z < Z) leftA += steps - stepA[z];
+        int leftB = leftA;
+        for (;;) {
+            if (!hx && leftA > 0) {
+                int bq = 0;
+                float xm = valA[0], runb = runA[0];
+                int stepb = stepA[0];
+#pragma unroll
+                for (int i = 1; i < NQ; i++)
+                    if (valA[i] < xm) { xm = valA[i]; bq = i; runb = runA[i]; stepb = stepA[i]; }
                 const int step = stepb + 1;
                 float nv = PINF, run = runb;
                 if (step < steps) {
-                    const int i = fwd ? step : L - 1 - step;
-                    const uint64_t mlo = w ? blo : alo, mhi = w ? bhi : ahi;
-                    int idx;
-                    run = __fadd_rn(asc_res(cfg, q, i, (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull), idx), runb);
-                    nv = pa_charge_mz(__dsub_rn(__dadd_rn((double)run, a1), a2), bq + 1);
+                    run = __fadd_rn(res_at(step, alo, ahi), runb);
+                    nv = frag(run, bq + 1);
                     if (nv < xm) mono = false;
                 }
 #pragma unroll
-                for (int i = 0; i < NQ; i++) {
-                    if (i == bq) {
-                        if (w) { runB[i] = run; stepB[i] = step; valB[i] = nv; }
-                        else { runA[i] = run; stepA[i] = step; valA[i] = nv; }
-                    }
-                }
-                if (w) { y = xm; hy = true; leftB--; } else { x = xm; hx = true; leftA--; }
+                for (int i = 0; i < NQ; i++)
+                    if (i == bq) { runA[i] = run; stepA[i] = step; valA[i] = nv; }
+                x = xm; hx = true; leftA--;
             }
-            if ((hx || leftA == 0) && (hy || leftB == 0)) {
-                if (!hx && !hy) break;
-                int takeA;                       // 1: A survives, 0: B survives, -1: both dropped
-                if (!hy) takeA = 1;
-                else if (!hx) takeA = 0;
-                else if (fabsf(__fsub_rn(x, y)) < cfg.err) takeA = -1;
-                else takeA = x < y;
-                if (takeA < 0) { hx = false; hy = false; }
-                else {
-                    const int hit = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, takeA ? x : y, cfg.err, cfg.err_gt_half) <= depth;
-                    if (takeA) { trialsA++; hitsA += hit; hx = false; }
-                    else { trialsB++; hitsB += hit; hy = false; }
+            if (!hy && leftB > 0) {
+                int bq = 0;
+                float xm = valB[0], runb = runB[0];
+                int stepb = stepB[0];
+#pragma unroll
+                for (int i = 1; i < NQ; i++)
+                    if (valB[i] < xm) { xm = valB[i]; bq = i; runb = runB[i]; stepb = stepB[i]; }
+                const int step = stepb + 1;
+                float nv = PINF, run = runb;
+                if (step < steps) {
+                    run = __fadd_rn(res_at(step, blo, bhi), runb);
+                    nv = frag(run, bq + 1);
+                    if (nv < xm) mono = false;
                 }
+#pragma unroll
+                for (int i = 0; i < NQ; i++)
+                    if (i == bq) { runB[i] = run; stepB[i] = step; valB[i] = nv; }
+                y = xm; hy = true; leftB--;
+            }
+            if (!hx && !hy) break;
+            int takeA;                       // 1: A survives, 0: B survives, -1: both dropped
+            if (!hy) takeA = 1;
+            else if (!hx) takeA = 0;
+            else if (fabsf(__fsub_rn(x, y)) < cfg.err) takeA = -1;
+            else takeA = x < y;
+            if (takeA < 0) { hx = false; hy = false; }
+            else {
+                asc_survivor(cfg, pk, depth, takeA ? x : y, takeA != 0, hitsA, trialsA, hitsB, trialsB);
+                if (takeA) hx = false; else hy = false;
             }
         }
         return mono;

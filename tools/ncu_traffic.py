@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""DRAM bytes per PSM of every kernel in an `ncu --page raw --csv` export -> JSON fragment for profiles/traffic.json.
+"""DRAM bytes and executed warp instructions per PSM of every kernel in an `ncu --page raw --csv` export
+-> JSON fragment for profiles/traffic.json.
     python tools/ncu_traffic.py raw.csv <psms per launch>"""
 import csv
 import json
@@ -18,7 +19,8 @@ for r in body:
         tot += float(r[ix[m]].replace(",", "")) * scale[units[ix[m]]]
     key = {"k_bin_topn": "bin_topn", "k_select": "select"}.get(name, "count_score" if name.startswith("k_count_score") else
                                                              "ascore" if name.startswith("k_ascore") else name)
-    e = out.setdefault(key, {"dram_bytes_per_psm": 0., "kernels": []})
+    e = out.setdefault(key, {"dram_bytes_per_psm": 0., "warp_inst_per_psm": 0., "kernels": []})
     e["dram_bytes_per_psm"] += tot / n
+    e["warp_inst_per_psm"] += float(r[ix["smsp__inst_executed.sum"]].replace(",", "")) / n
     e["kernels"].append(name)
 print(json.dumps(out, indent=1))
