@@ -403,8 +403,6 @@ struct PaPlanOut {
     int* max_frag;           // max fragments per isoform (all types/charges) over the chunk
     int* max_list;           // max fragments per (isoform, type) over the chunk (K3 list size)
     int* max_len;            // longest scored peptide of the chunk
-    uint8_t* sort_key;       // [n_psm] peptide length (order in which k_select visits the PSMs)
-    int32_t* sort_idx;       // [n_psm] identity
 };
 
 __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n_psm, PaPlanOut o) {
@@ -448,8 +446,6 @@ __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n
         }
     }
     o.psm_S[p] = S;
-    o.sort_key[p] = (uint8_t)(L < 0 ? 0 : (L > 255 ? 255 : L));
-    o.sort_idx[p] = (int32_t)p;
     o.psm_status[p] = status;
     o.psm_I[p] = I;
     o.psm_units[p] = (int32_t)((I + PA_UNIT - 1) / PA_UNIT);
@@ -484,7 +480,8 @@ struct PaCountArgs {
     const int32_t* psm_status;
     PaIso iso;
     unsigned long long* n_lookups;   // counter
-    unsigned long long* next_unit;   // work cursor (zeroed before the launch): warps grab PA_K2_GRAB units at a time
+    unsigned long long* next_unit;   // work cursor (zeroed before the launch): warps take `grab` units at a time
+    int grab;                        // 1 .. PA_K2_GRAB units per grab; negative: do not reserve the next grab ahead
 };
 
 #ifndef PA_K2_MINBLOCKS
@@ -633,15 +630,19 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
     unsigned long long lookups = 0;
     const int T = PAIR ? 2 : 1;
     // Units differ in cost by two orders of magnitude (1 .. 1024 isoforms), so they are handed out
-    // dynamically: a warp takes PA_K2_GRAB consecutive units from a global cursor and asks for its next
+    // dynamically: a warp takes `grab` consecutive units from a global cursor and asks for its next
     // grab before it starts on the current one (the atomic's round trip hides behind the work).
     (void)gw; (void)nw;
     unsigned long long pend = 0;
-    if (lane == 0) pend = atomicAdd(a.next_unit, (unsigned long long)PA_K2_GRAB);
+    const int grab = a.grab < 0 ? -a.grab : a.grab;
+    if (lane == 0) pend = atomicAdd(a.next_unit, (unsigned long long)grab);
     int64_t base = (int64_t)__shfl_sync(PA_FULL, pend, 0);
+    // (with few units per warp -- grab < 0 -- the next grab is only taken when this one is done: a unit held
+    // in reserve by a busy warp would wait while other warps sit idle)
+    const bool ahead = a.grab > 0;
     while (base < a.n_units) {
-      if (lane == 0) pend = atomicAdd(a.next_unit, (unsigned long long)PA_K2_GRAB);
-      const int64_t u_end = base + PA_K2_GRAB < a.n_units ? base + PA_K2_GRAB : a.n_units;
+      if (ahead && lane == 0) pend = atomicAdd(a.next_unit, (unsigned long long)grab);
+      const int64_t u_end = base + grab < a.n_units ? base + grab : a.n_units;
       for (int64_t u = base; u < u_end; u++) {
         const int64_t p = a.unit_psm[u];
         const int64_t I = a.iso_off[p + 1] - a.iso_off[p];
@@ -689,6 +690,7 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
             }
         }
       }
+      if (!ahead && lane == 0) pend = atomicAdd(a.next_unit, (unsigned long long)grab);
       base = (int64_t)__shfl_sync(PA_FULL, pend, 0);
     }
     for (int o = 16; o > 0; o >>= 1) lookups += __shfl_xor_sync(PA_FULL, lookups, o);
@@ -735,16 +737,21 @@ struct PaSelArgs {
     uint32_t* best_idx;          // [n_psm] best isoform (lexicographic rank), 0xffffffff = none
     int32_t* mod_psm;            // [entries] chunk-relative PSM of each mod entry, -1 = no Ascore to compute
     unsigned long long* tie;     // [entries] tied best competitors of each mod entry
-    int32_t* work_list;          // [4][work_cap] entries whose Ascore needs the site-determining-ion comparison,
-    int* work_count;             // [4]              by stream class (k_ascore)
-    int64_t work_cap;
-    const int32_t* order;        // [n_psm] PSMs by peptide length: neighbouring Ascore entries then run
-                                 //         merges of similar length, which keeps k_ascore's warps converged
-    unsigned long long* next_psm;    // work cursor into `order` (zeroed before the launch)
+    uint16_t* work_key;          // [entries] sort key of each mod entry: stream class << 10 | (1023 - estimated merge
+    int32_t* work_val;           // [entries]   trips), PA_WORK_NONE = no site-determining-ion comparison needed; identity
+    int* work_count;             // [4] entries per stream class (k_ascore)
+    const int32_t* order;        // optional visiting order of the PSMs (null = input order)
+    unsigned long long* next_psm;    // work cursor (zeroed before the launch)
+    int grab;                        // PSMs per visit to the cursor: 1 .. PA_SEL_GRAB; negative: no reservation ahead
 };
 #ifndef PA_SEL_GRAB
 #define PA_SEL_GRAB 16
 #endif
+#define PA_WORK_BITS 13
+#ifndef PA_WORK_SHIFT
+#define PA_WORK_SHIFT 5      // low bits of the trip estimate dropped from the key (coarser classes keep more input order)
+#endif
+#define PA_WORK_NONE 0x1fffu
 
 // --- libstdc++ std::sort (introsort + final insertion sort), comparator a.w > b.w ------------
 // bits/stl_algo.h of GCC 13, as in SURVEY.md appendix A.2.  Elements are (float w, uint32 id)
@@ -1027,19 +1034,6 @@ __device__ __forceinline__ void pa_depth_scores(const PaCfg& cfg, unsigned long 
     for (int d = 0; d < PA_N_TOP; d++) sc[d] = __ldg(cfg.T + pa_tab_index(n, pa_cum_get(lo, hi, d), d));
 }
 
-// append the n buffered Ascore entries of class c to its global list (one atomic per flush)
-__device__ __forceinline__ void pa_flush_queue(const PaSelArgs& a, const int32_t* s_q, int c, int n) {
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    if (n > 0) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(a.work_count + c, n);
-        base = __shfl_sync(PA_FULL, base, 0);
-        if (lane < n) a.work_list[(int64_t)c * a.work_cap + base + lane] = s_q[lane];
-    }
-    __syncwarp();
-}
-
 // K3a: warp per PSM.  Best isoform in the reference's order + per modified site the set of tied
 // best competitors (= alternative sites).  The Ascore of every (PSM, site) entry is then computed
 // by k_ascore (thread per entry) or, for the rare shapes that kernel does not cover, k_ascore_generic.
@@ -1047,23 +1041,23 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned long long* s_sort = (unsigned long long*)smem_raw + (size_t)wib * PA_SORTCAP;
-    __shared__ int32_t s_queue_all[8][4][32];         // per warp and stream class: one k_ascore warp's worth
-    int32_t (*s_queue)[32] = s_queue_all[wib];
-    int qn0 = 0, qn1 = 0, qn2 = 0, qn3 = 0;           // entries buffered per class (lane-uniform)
+    __shared__ uint8_t s_pos_all[8][64];              // per warp: residue index of each site of the current PSM
+    uint8_t* s_pos = s_pos_all[wib];
+    int qn0 = 0, qn1 = 0, qn2 = 0, qn3 = 0;           // Ascore entries found per stream class (lane-uniform)
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const float INF = __int_as_float(0x7f800000);
 
-    // Warps take runs of PA_SEL_GRAB consecutive PSMs of the length-ordered list from a global cursor
-    // (the cost per PSM grows with its isoform count, so a static split leaves warps idle).  All warps
-    // advance through the list together, so the 32 entries a warp appends per flush -- one k_ascore
-    // warp -- still stem from peptides of (nearly) the same length.
+    // Warps take runs of `grab` consecutive PSMs from a global cursor (the cost per PSM grows with
+    // its isoform count, so a static split leaves warps idle).
     (void)gw; (void)nw;
     unsigned long long pend = 0;
-    if (lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)PA_SEL_GRAB);
+    const int grab = a.grab < 0 ? -a.grab : a.grab;
+    if (lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)grab);
     int64_t run0 = (int64_t)__shfl_sync(PA_FULL, pend, 0);
+    const bool ahead = a.grab > 0;                    // see k_count_score
     while (run0 < a.n_psm) {
-      if (lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)PA_SEL_GRAB);
-      const int64_t pi_end = run0 + PA_SEL_GRAB < a.n_psm ? run0 + PA_SEL_GRAB : a.n_psm;
+      if (ahead && lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)grab);
+      const int64_t pi_end = run0 + grab < a.n_psm ? run0 + grab : a.n_psm;
       for (int64_t pi = run0; pi < pi_end; pi++) {
         const int64_t p = a.order ? a.order[pi] : pi;
         const int status = a.psm_status[p];
@@ -1093,8 +1087,28 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 if (a.ascores) a.ascores[mo + j] = fill;
                 if (a.alt_sites) a.alt_sites[mo + j] = 0;
                 a.mod_psm[mo + j - a.mod_lo] = -1;
+                a.work_key[mo + j - a.mod_lo] = (uint16_t)PA_WORK_NONE;
+                a.work_val[mo + j - a.mod_lo] = (int32_t)(mo + j - a.mod_lo);
             }
             continue;
+        }
+        // residue positions of the sites: the distance between two sites is what an Ascore merge costs
+        const int pep0 = b.pep_off[p], L = b.pep_off[p + 1] - pep0;
+        if (a.ascores) {
+            int ns = 0;
+            __syncwarp();
+            for (int base = 0; base < L; base += 32) {
+                const int i = base + lane;
+                bool is = false;
+                if (i < L) {
+                    const int c = (int)b.pep[pep0 + i] - 'A';
+                    is = ((c >= 0 && c < 26) && ((cfg.mod_letters >> c) & 1u)) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == L - 1);
+                }
+                const unsigned bal = __ballot_sync(PA_FULL, is);
+                if (is) { const int j = ns + __popc(bal & ((1u << lane) - 1u)); if (j < 64) s_pos[j] = (uint8_t)i; }
+                ns += __popc(bal);
+            }
+            __syncwarp();
         }
         // ---- best isoform ---------------------------------------------------------------
         float wmax = -INF;
@@ -1168,29 +1182,43 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                 }
             }
             if (a.ascores) {
-                // everything else is queued for k_ascore, by stream count so that the lanes of a
-                // k_ascore warp run the same code.  Entries collect in a per-warp buffer and are
-                // appended to the global lists 32 at a time (one atomic per class and flush).
+                // everything else goes to k_ascore.  Every entry gets a sort key -- stream class (so that
+                // the lanes of a k_ascore warp run the same code), then the estimated number of merge trips,
+                // longest first: per tied competitor one trip per residue plus three per residue between the
+                // two sites, times the charges -- and the host sorts the entries by it, so that the lanes of a
+                // warp also finish together.
                 const float wb = a.iso.w[ib + best];
+                uint32_t key = PA_WORK_NONE;
                 if (!((double)fabsf(__fsub_rn(wb, m)) < 1e-6)) {
                     const int Z = b.max_charge[p];
                     const int cls = cfg.has_nl ? 3 : (Z == 1 ? 0 : (Z == 2 ? 1 : (Z <= 4 ? 2 : 3)));
                     int& qn = cls == 0 ? qn0 : (cls == 1 ? qn1 : (cls == 2 ? qn2 : qn3));
-                    if (lane == 0) s_queue[cls][qn] = (int32_t)(mo + j - a.mod_lo);
                     qn++;
-                    // a full buffer is exactly one k_ascore warp: 32 entries of one class from
-                    // neighbouring PSMs of the length-ordered visit, i.e. merges of equal shape
-                    if (qn == 32) { pa_flush_queue(a, s_queue[cls], cls, 32); qn = 0; }
+                    int work = 0;
+                    const int ps = s_pos[site < 64 ? site : 63];
+                    for (uint64_t tt = tie; tt; tt &= tt - 1) {
+                        const int pu = s_pos[__ffsll((long long)tt) - 1];
+                        work += (L - 1) + 3 * (pu > ps ? pu - ps : ps - pu);
+                    }
+                    work *= Z < 8 ? Z : 8;
+                    key = ((uint32_t)cls << 10) | (((uint32_t)(1023 - (work > 1023 ? 1023 : work)) >> PA_WORK_SHIFT) << PA_WORK_SHIFT);
+                }
+                if (lane == 0) {
+                    a.work_key[mo + j - a.mod_lo] = (uint16_t)key;
+                    a.work_val[mo + j - a.mod_lo] = (int32_t)(mo + j - a.mod_lo);
                 }
             }
         }
         __syncwarp();
       }
+      if (!ahead && lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)grab);
       run0 = (int64_t)__shfl_sync(PA_FULL, pend, 0);
     }
-    if (a.ascores) {
-        pa_flush_queue(a, s_queue[0], 0, qn0); pa_flush_queue(a, s_queue[1], 1, qn1);
-        pa_flush_queue(a, s_queue[2], 2, qn2); pa_flush_queue(a, s_queue[3], 3, qn3);
+    if (a.ascores && lane == 0) {
+        if (qn0) atomicAdd(a.work_count + 0, qn0);
+        if (qn1) atomicAdd(a.work_count + 1, qn1);
+        if (qn2) atomicAdd(a.work_count + 2, qn2);
+        if (qn3) atomicAdd(a.work_count + 3, qn3);
     }
 }
 
@@ -1216,9 +1244,8 @@ struct PaAscArgs {
     const int32_t* psm_S;
     PaIso iso;
     float* ascores;              // absolute-indexed output (may be null)
-    const int32_t* work_list;    // [4][work_cap] entries queued by k_select, by stream class
-    const int* work_count;       // [4]
-    int64_t work_cap;
+    const int32_t* work_sorted;  // mod entries sorted by k_select's key: class 0 first, longest merges first
+    const int* work_count;       // [4] entries per stream class
     int32_t* generic_list;       // entries that need the generic kernel
     int* generic_count;
 };
@@ -1679,7 +1706,10 @@ template <int NQ, int CLS>
 __global__ void __launch_bounds__(128, (NQ <= 2 ? PA_ASC_MINBLOCKS : 4)) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.work_count[CLS]) return;
-    asc_entry<NQ>(cfg, b, a, a.work_list[(int64_t)CLS * a.work_cap + w]);
+    int64_t first = 0;                       // classes are contiguous in the sorted list
+#pragma unroll
+    for (int c = 0; c < CLS; c++) first += a.work_count[c];
+    asc_entry<NQ>(cfg, b, a, a.work_sorted[first + w]);
 }
 
 // K3c: generic (warp-cooperative, list-materialising) Ascore for the entries k_ascore queued.

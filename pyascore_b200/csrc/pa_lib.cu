@@ -58,9 +58,9 @@ struct Slot {                // per-stream working set
     // K1
     DevBuf rmz, rrank, rcount, ctab, chead, g_bin, g_tmp;
     // plan
-    DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp, sort_key, sort_idx, sort_key2, order;
+    DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
     // K2/K3
-    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, sched, best_idx, mod_psm, tie, generic_list, generic_count, work_list;
+    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, sched, best_idx, mod_psm, tie, generic_list, generic_count, work_key, work_key2, work_val, work_sorted;
     // staged outputs
     DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
     PlanTotals* h_totals = nullptr;      // pinned
@@ -69,8 +69,8 @@ struct Slot {                // per-stream working set
     void release() {
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
-                         &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &sort_key, &sort_idx, &sort_key2, &order, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_list, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
+                         &iso_w, &g_sort, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_totals) cudaFreeHost(h_totals);
@@ -132,6 +132,15 @@ static int resident_blocks(K kernel, int threads, size_t smem) {
         n = 1;
     }
     return n;
+}
+
+// Items a warp of a persistent kernel takes per visit to the work cursor: up to `most` when every warp
+// has at least eight visits' worth; with fewer than four items per warp the sign is flipped, which
+// tells the kernel not to reserve its next grab ahead of time.
+static int grab_size(int64_t items, int64_t warps, int most) {
+    const int64_t per_warp = items / std::max<int64_t>(warps, 1);
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(most, per_warp / 8));
+    return per_warp < 4 ? -g : g;
 }
 
 // Launch shape of k_bin_topn for spectra of up to `max_peaks` peaks: slot capacity, warps per block
@@ -682,9 +691,6 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     PaPlanOut po;
     po.psm_S = sl.psm_S.as<int32_t>(); po.psm_status = sl.psm_status.as<int32_t>();
     po.psm_I = sl.psm_I.as<int64_t>(); po.psm_units = sl.psm_units.as<int32_t>();
-    CK(sl.sort_key.ensure((size_t)(np + 1))); CK(sl.sort_key2.ensure((size_t)(np + 1)));
-    CK(sl.sort_idx.ensure((size_t)(np + 1) * 4)); CK(sl.order.ensure((size_t)(np + 1) * 4));
-    po.sort_key = sl.sort_key.as<uint8_t>(); po.sort_idx = sl.sort_idx.as<int32_t>();
     PlanTotals* dt = sl.totals.as<PlanTotals>();
     po.combo_bits = dt->combo_bits; po.max_frag = &dt->max_frag; po.max_list = &dt->max_list; po.max_len = &dt->max_len;
     if (np > 0) {
@@ -692,23 +698,15 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
         CK(cudaGetLastError());
         s->ctr.kernel_launches++;
     }
-    size_t t1 = 0, t2 = 0, t3 = 0;
+    size_t t1 = 0, t2 = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, t1, po.psm_I, sl.iso_off.as<int64_t>(), (int)(np + 1), st));
     CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, po.psm_units, sl.unit_off.as<int32_t>(), (int)(np + 1), st));
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, t3, po.sort_key, sl.sort_key2.as<uint8_t>(), po.sort_idx,
-                                       sl.order.as<int32_t>(), (int)np, 0, 8, st));
-    CK(sl.cub_tmp.ensure(std::max(std::max(t1, t2), t3) + 256));
+    CK(sl.cub_tmp.ensure(std::max(t1, t2) + 256));
     size_t tb = sl.cub_tmp.cap;
     CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, tb, po.psm_I, sl.iso_off.as<int64_t>(), (int)(np + 1), st));
     tb = sl.cub_tmp.cap;
     CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, tb, po.psm_units, sl.unit_off.as<int32_t>(), (int)(np + 1), st));
     s->ctr.kernel_launches += 2;
-    if (np > 0) {      // PSMs by peptide length, for k_select (stable: equal lengths stay in input order)
-        tb = sl.cub_tmp.cap;
-        CK(cub::DeviceRadixSort::SortPairs(sl.cub_tmp.p, tb, po.sort_key, sl.sort_key2.as<uint8_t>(), po.sort_idx,
-                                           sl.order.as<int32_t>(), (int)np, 0, 8, st));
-        s->ctr.kernel_launches += 3;
-    }
     CK(cudaMemcpyAsync(&dt->total_iso, sl.iso_off.as<int64_t>() + np, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(&dt->total_units, sl.unit_off.as<int32_t>() + np, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(sl.h_totals, dt, sizeof(PlanTotals), cudaMemcpyDeviceToHost, st));
@@ -767,6 +765,7 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         // One resident wave of blocks; the warps pull units from the cursor.
 #define PA_K2_LAUNCH(NL, PR, EG) { \
             int blocks = (int)std::min<int64_t>(want, (int64_t)s->sm_count * resident_blocks(k_count_score<NL, PR, EG>, wpb * 32, smem)); \
+            ca.grab = grab_size(n_units, (int64_t)blocks * wpb, PA_K2_GRAB); \
             k_count_score<NL, PR, EG><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); }
         const int variant = (s->cfg.has_nl ? 4 : 0) | (pair ? 2 : 0) | (s->cfg.err_gt_half ? 1 : 0);
         switch (variant) {
@@ -797,7 +796,8 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     CK(sl.mod_psm.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
     CK(sl.tie.ensure((size_t)std::max<int64_t>(nm, 1) * 8));
     CK(sl.generic_list.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
-    CK(sl.work_list.ensure((size_t)std::max<int64_t>(nm, 1) * 4 * 4));
+    CK(sl.work_key.ensure((size_t)std::max<int64_t>(nm, 1) * 2)); CK(sl.work_key2.ensure((size_t)std::max<int64_t>(nm, 1) * 2));
+    CK(sl.work_val.ensure((size_t)std::max<int64_t>(nm, 1) * 4)); CK(sl.work_sorted.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
     CK(sl.generic_count.ensure(32));                 // [0] generic entries, [1..4] k_ascore work entries by class
     CK(cudaMemsetAsync(sl.generic_count.p, 0, 32, st));
     cs.e_asc1 = next_event(s);
@@ -816,13 +816,14 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.g_sort = sl.g_sort.as<unsigned long long>();
         sa.mod_lo = cs.mod_lo; sa.best_idx = sl.best_idx.as<uint32_t>(); sa.mod_psm = sl.mod_psm.as<int32_t>();
         sa.tie = sl.tie.as<unsigned long long>();
-        sa.work_list = sl.work_list.as<int32_t>(); sa.work_count = sl.generic_count.as<int>() + 1;
-        sa.work_cap = std::max<int64_t>(nm, 1);
-        sa.order = sl.order.as<int32_t>();
+        sa.work_key = sl.work_key.as<uint16_t>(); sa.work_val = sl.work_val.as<int32_t>();
+        sa.work_count = sl.generic_count.as<int>() + 1;
+        sa.order = nullptr;                      // PSMs in input order: the Ascore entries are sorted by key below
         sa.next_psm = sl.sched.as<unsigned long long>() + 1;
         const int wpb = 8;
         const size_t sel_smem = wpb * PA_SORTCAP * sizeof(unsigned long long);
         int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * resident_blocks(k_select, wpb * 32, sel_smem));
+        sa.grab = grab_size(np, (int64_t)blocks * wpb, PA_SEL_GRAB);
         k_select<<<blocks, wpb * 32, sel_smem, st>>>(s->cfg, cs.b, sa);
         CK(cudaGetLastError());
         s->ctr.kernel_launches++; s->ctr.launches_select++;
@@ -835,8 +836,16 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         aa.mod_off = cs.mod_off_abs; aa.iso_off = sl.iso_off.as<int64_t>(); aa.psm_S = sl.psm_S.as<int32_t>();
         aa.iso = iso; aa.ascores = cs.o_asc; aa.generic_list = sl.generic_list.as<int32_t>();
         aa.generic_count = sl.generic_count.as<int>();
-        aa.work_list = sl.work_list.as<int32_t>(); aa.work_count = sl.generic_count.as<int>() + 1;
-        aa.work_cap = std::max<int64_t>(nm, 1);
+        aa.work_sorted = sl.work_sorted.as<int32_t>(); aa.work_count = sl.generic_count.as<int>() + 1;
+        // Ascore entries by stream class, longest merges first (keys written by k_select)
+        size_t tw = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tw, sl.work_key.as<uint16_t>(), sl.work_key2.as<uint16_t>(),
+                                           sl.work_val.as<int32_t>(), sl.work_sorted.as<int32_t>(), (int)nm, 0, PA_WORK_BITS, st));
+        CK(sl.cub_tmp.ensure(tw + 256));
+        tw = sl.cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(sl.cub_tmp.p, tw, sl.work_key.as<uint16_t>(), sl.work_key2.as<uint16_t>(),
+                                           sl.work_val.as<int32_t>(), sl.work_sorted.as<int32_t>(), (int)nm, 0, PA_WORK_BITS, st));
+        s->ctr.kernel_launches += 3;
         const unsigned ab = (unsigned)((nm + 127) / 128);
         if (!s->cfg.has_nl) {
             k_ascore<1, 0><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
