@@ -90,6 +90,9 @@ struct PaBinArgs {
 //                 tie masks u32[128] sit at 4 cap and ranks u8[cap] at 4 cap + 512
 //   bin u8[cap] | bstart u16[128] | bend u16[128] | cell u8[256]
 #define PA_BIN_MINCAP 192
+#ifndef PA_K1_UNROLL
+#define PA_K1_UNROLL 2       // interior groups of the rank walk per trip (bins hold ~5 groups: deeper unrolling only adds remainders)
+#endif
 #define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 17 + PA_NBIN_SMEM * 4 + PA_NCELL)
 
 __device__ __forceinline__ void pa_cp_async8(void* smem_dst, const void* gsrc) {
@@ -151,51 +154,72 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             bounds();
             fast = n_bins <= PA_NBIN_SMEM;
         }
+        // The binning and output passes give every lane two neighbouring peaks (i0 = base + 2 lane,
+        // i1 = i0 + 1): one 16-byte shared-memory access serves both and the per-round overhead is halved.
         if (fast) {
-            // bins, float m/z and intensity keys; a sorted spectrum makes every bin one contiguous
+            // bins, float m/z and ranking keys; a sorted spectrum makes every bin one contiguous
             // run [bstart, bend).  Sortedness is checked on what the fast path relies on:
             // non-decreasing bins and non-decreasing (float)m/z.
             bool sorted = true;
             const double inv_bs = __ddiv_rn(1.0, dbs);
             int carry_bin = -1;
             float carry_mz = -INFINITY;
-            for (int base = 0; base < P; base += 32) {
-                const int i = base + lane;
-                int bq = 0x7fffffff;
-                float mzf = INFINITY;
-                float hi = 0.f;
-                if (i < P) {
-                    const double m = s_mz[i];
+            auto bin_of = [&](double m) {
+                const double x = __dsub_rn(m, dmin);
+                // floor(x / bin_size) as the reference computes it; the reciprocal product decides
+                // unless it lands within 1e-9 of an integer, where the IEEE quotient is taken
+                double t = __dmul_rn(x, inv_bs);
+                double q = floor(t);
+                const double fr = __dsub_rn(t, q);
+                if (!(fr > 1e-9 && fr < 1. - 1e-9)) q = floor(__ddiv_rn(x, dbs));
+                long long b64 = (long long)q;
+                if (b64 > n_bins - 1) b64 = n_bins - 1;
+                if (b64 < 0) b64 = 0;               // only reachable for unsorted input (general path follows)
+                return (int)b64;
+            };
+            for (int base = 0; base < P; base += 64) {
+                const int i0 = base + 2 * lane, i1 = i0 + 1;
+                const bool v0 = i0 < P, v1 = i1 < P;
+                int bq0 = 0x7fffffff, bq1 = 0x7fffffff;
+                float mz0 = INFINITY, mz1 = INFINITY, k0 = 0.f, k1 = 0.f;
+                if (v0) {
+                    // (the second element of the pair may lie past the spectrum: still inside the slot)
+                    const double2 m2 = *(const double2*)&s_mz[i0];
+                    const double2 t2 = *(const double2*)&s_key[i0];
+                    if (m2.x < mn || m2.x > mx) sorted = false;      // the ends must be the true extremes
+                    bq0 = bin_of(m2.x);
+                    mz0 = __double2float_rn(m2.x);
                     // ranking key: the intensity rounded to float.  The rounding is monotone, so two peaks
                     // with different keys are ordered as their doubles are, and peaks of one bin that
                     // share a key (ties, +-0, NaN) are caught below and ranked on the doubles instead
-                    hi = __double2float_rn(__longlong_as_double((long long)s_key[i]));
-                    if (m < mn || m > mx) sorted = false;     // the ends must be the true extremes
-                    const double x = __dsub_rn(m, dmin);
-                    // floor(x / bin_size) as the reference computes it; the reciprocal product decides
-                    // unless it lands within 1e-9 of an integer, where the IEEE quotient is taken
-                    double t = __dmul_rn(x, inv_bs);
-                    double q = floor(t);
-                    const double fr = __dsub_rn(t, q);
-                    if (!(fr > 1e-9 && fr < 1. - 1e-9)) q = floor(__ddiv_rn(x, dbs));
-                    long long b64 = (long long)q;
-                    if (b64 > n_bins - 1) b64 = n_bins - 1;
-                    if (b64 < 0) b64 = 0;           // only reachable for unsorted input (general path follows)
-                    bq = (int)b64;
-                    mzf = __double2float_rn(m);
+                    k0 = __double2float_rn(t2.x);
+                    if (v1) {
+                        if (m2.y < mn || m2.y > mx) sorted = false;
+                        bq1 = bin_of(m2.y);
+                        mz1 = __double2float_rn(m2.y);
+                        k1 = __double2float_rn(t2.y);
+                        if (bq1 < bq0 || mz1 < mz0) sorted = false;
+                    }
                 }
                 __syncwarp();                       // every lane has read its staging slots
-                if (i < P) { s_mzf[i] = mzf; s_hi[i] = hi; s_bin[i] = (uint8_t)bq; }
-                int bprev = __shfl_up_sync(PA_FULL, bq, 1);
-                float mprev = __shfl_up_sync(PA_FULL, mzf, 1);
-                if (lane == 0) { bprev = carry_bin; mprev = carry_mz; }
-                if (i < P) {
-                    if (bq < bprev || mzf < mprev) sorted = false;
-                    if (bq != bprev) { s_bstart[bq] = (uint16_t)i; if (i > 0 && bprev >= 0 && bprev < PA_NBIN_SMEM) s_bend[bprev] = (uint16_t)i; }
-                    if (i == P - 1) s_bend[bq] = (uint16_t)P;
+                if (v0) {
+                    *(float2*)&s_mzf[i0] = make_float2(mz0, mz1);
+                    *(float2*)&s_hi[i0] = make_float2(k0, k1);
+                    *(uchar2*)&s_bin[i0] = make_uchar2((unsigned char)bq0, (unsigned char)bq1);
                 }
-                carry_bin = __shfl_sync(PA_FULL, bq, 31);
-                carry_mz = __shfl_sync(PA_FULL, mzf, 31);
+                // bin and m/z of the preceding peak: the last valid peak of the lane below
+                int bprev = __shfl_up_sync(PA_FULL, v1 ? bq1 : bq0, 1);
+                float mprev = __shfl_up_sync(PA_FULL, v1 ? mz1 : mz0, 1);
+                if (lane == 0) { bprev = carry_bin; mprev = carry_mz; }
+                if (v0) {
+                    if (bq0 < bprev || mz0 < mprev) sorted = false;
+                    if (bq0 != bprev) { s_bstart[bq0] = (uint16_t)i0; if (i0 > 0 && bprev >= 0 && bprev < PA_NBIN_SMEM) s_bend[bprev] = (uint16_t)i0; }
+                    if (v1 && bq1 != bq0) { s_bstart[bq1] = (uint16_t)i1; s_bend[bq0] = (uint16_t)i1; }
+                    if (i0 == P - 1) s_bend[bq0] = (uint16_t)P;
+                    if (i1 == P - 1) s_bend[bq1] = (uint16_t)P;
+                }
+                carry_bin = __shfl_sync(PA_FULL, bq1, 31);
+                carry_mz = __shfl_sync(PA_FULL, mz1, 31);
             }
             fast = __all_sync(PA_FULL, sorted);
             __syncwarp();
@@ -222,6 +246,16 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             // Two peaks of a bin with the same key get the same count: every kept peak marks its
             // count in the bin's mask, and a mark found already set flags the bin for exact ranking.
             const float4* h4 = (const float4*)s_hi;
+            constexpr int kRankUnroll = PA_K1_UNROLL;
+            const float NINF = __int_as_float(0xff800000);
+            auto mark = [&](int bq, int cnt) {
+                if (cnt < n_top) {
+                    const uint32_t bit = 1u << cnt;
+                    if (atomicOr(&s_bmask[bq], bit) & bit) atomicOr(&s_bmask[bq], 0x80000000u);
+                }
+            };
+            // (one peak per lane here: the lanes of a round walk their bins in lock step, so a second
+            // peak per lane would only double the work of every trip)
             for (int base = 0; base < P; base += 32) {
                 const int i = base + lane;
                 if (i < P) {
@@ -233,13 +267,13 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                         const float hi = s_hi[i];
                         const unsigned n = (unsigned)(b1 - b0);
                         const int g0 = b0 >> 2, gl = (b1 - 1) >> 2;
-                        const float NINF = __int_as_float(0xff800000);
                         float4 v = h4[g0];
                         int r = (g0 << 2) - b0;
                         v.x = (unsigned)r < n ? v.x : NINF; v.y = (unsigned)(r + 1) < n ? v.y : NINF;
                         v.z = (unsigned)(r + 2) < n ? v.z : NINF; v.w = (unsigned)(r + 3) < n ? v.w : NINF;
                         // one compare-to-1.0f and one add per peak; the sums are small integers, exact in float
                         float c = (v.x > hi ? 1.f : 0.f) + (v.y > hi ? 1.f : 0.f) + (v.z > hi ? 1.f : 0.f) + (v.w > hi ? 1.f : 0.f);
+#pragma unroll kRankUnroll
                         for (int g = g0 + 1; g < gl; g++) {
                             v = h4[g];
                             c += (v.x > hi ? 1.f : 0.f) + (v.y > hi ? 1.f : 0.f) + (v.z > hi ? 1.f : 0.f) + (v.w > hi ? 1.f : 0.f);
@@ -252,36 +286,46 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                             c += (v.x > hi ? 1.f : 0.f) + (v.y > hi ? 1.f : 0.f) + (v.z > hi ? 1.f : 0.f) + (v.w > hi ? 1.f : 0.f);
                         }
                         cnt = (int)c;
-                        if (cnt < n_top) {
-                            const uint32_t bit = 1u << cnt;
-                            if (atomicOr(&s_bmask[bq], bit) & bit) atomicOr(&s_bmask[bq], 0x80000000u);
-                        }
+                        mark(bq, cnt);
                     }
                     s_cnt[i] = (uint8_t)(cnt < n_top ? cnt : 255);
                 }
             }
             __syncwarp();
             int out = 0;
-            for (int base = 0; base < P; base += 32) {
-                const int i = base + lane;
-                int cnt = 255, bq = 0;
-                float mzf = 0.f;
-                if (i < P) {
-                    mzf = s_mzf[i];
-                    bq = s_bin[i];
-                    cnt = s_cnt[i];
-                    if (!exact_all && (s_bmask[bq] >> 31)) cnt = exact_rank(i, s_bstart[bq], s_bend[bq]);
+            for (int base = 0; base < P; base += 64) {
+                const int i0 = base + 2 * lane, i1 = i0 + 1;
+                int cnt0 = 255, cnt1 = 255, bq0 = 0, bq1 = 0;
+                float mz0 = 0.f, mz1 = 0.f;
+                if (i0 < P) {
+                    const float2 mm = *(const float2*)&s_mzf[i0];
+                    const uchar2 bb = *(const uchar2*)&s_bin[i0];
+                    const uchar2 cc = *(const uchar2*)&s_cnt[i0];
+                    mz0 = mm.x; mz1 = mm.y; bq0 = bb.x; bq1 = bb.y; cnt0 = cc.x;
+                    if (!exact_all && (s_bmask[bq0] >> 31)) cnt0 = exact_rank(i0, s_bstart[bq0], s_bend[bq0]);
+                    if (i1 < P) {
+                        cnt1 = cc.y;
+                        if (!exact_all && (s_bmask[bq1] >> 31)) cnt1 = exact_rank(i1, s_bstart[bq1], s_bend[bq1]);
+                    }
                 }
-                const bool keep = cnt < n_top;
-                unsigned bal = __ballot_sync(PA_FULL, keep);   // every lane has read its own s_mzf entry by now
-                if (keep) {
-                    int pos = out + __popc(bal & ((1u << lane) - 1u));
-                    a.rmz[off + pos] = mzf;
-                    a.rrank[off + pos] = (uint8_t)cnt;
-                    if (a.rindex) { a.rindex[off + pos] = i; a.rbin[off + pos] = bq; }
-                    s_mzf[pos] = mzf;               // pos <= i: only entries this or earlier chunks own
+                const bool keep0 = cnt0 < n_top, keep1 = cnt1 < n_top;
+                const unsigned bal0 = __ballot_sync(PA_FULL, keep0), bal1 = __ballot_sync(PA_FULL, keep1);
+                const unsigned below = (1u << lane) - 1u;       // every lane has read its own entries by now
+                int pos = out + __popc(bal0 & below) + __popc(bal1 & below);
+                if (keep0) {
+                    a.rmz[off + pos] = mz0;
+                    a.rrank[off + pos] = (uint8_t)cnt0;
+                    if (a.rindex) { a.rindex[off + pos] = i0; a.rbin[off + pos] = bq0; }
+                    s_mzf[pos] = mz0;               // pos <= i0: only entries this or earlier rounds own
+                    pos++;
                 }
-                out += __popc(bal);
+                if (keep1) {
+                    a.rmz[off + pos] = mz1;
+                    a.rrank[off + pos] = (uint8_t)cnt1;
+                    if (a.rindex) { a.rindex[off + pos] = i1; a.rbin[off + pos] = bq1; }
+                    s_mzf[pos] = mz1;
+                }
+                out += __popc(bal0) + __popc(bal1);
                 __syncwarp();
             }
             const float* s_out = s_mzf;
