@@ -174,8 +174,7 @@ struct PsmSmem {
 struct PsmInfo {
     int L, k, Z, S, R;
     int status;
-    const float* pm;              // global peaks (used when they are not staged: cell == nullptr)
-    const uint8_t* pr;
+    const float2* gp;             // global peaks {mz, rank bits} (used when they are not staged: cell == nullptr)
     const float2* pk;             // staged peaks in shared memory (cell != nullptr)
     const uint8_t* cell;          // -> smem cell index, or nullptr (binary search over global peaks)
     float cell_base, cell_inv;    // cell(x) = clamp(floor((x - base) * inv), 0, PA_NCELL-1)
@@ -206,14 +205,18 @@ struct PaBatchDev {               // device views of one chunk
     const int32_t* aux_off;       // may be null
     const uint32_t* aux_pos;
     const float* aux_mass;
-    const float* rmz;             // K1 output, indexed with spec_off
-    const uint8_t* rrank;
+    const float2* rpk;            // K1 output, indexed with spec_off: retained peaks {(float)mz ascending, rank as int bits}
     const int32_t* rcount;
     const uint8_t* ctab;          // per spectrum PA_NCELL bytes: first retained peak at or after each m/z cell
     const float2* chead;          // per spectrum {cell base, 1/cell width}; width 0 = no table (binary search)
     int64_t spec_base;            // spec_off values are relative to this peak index
     int64_t n_spec;
 };
+
+__device__ __forceinline__ void pa_cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 
 // Build the residue / neutral-loss / site tables of PSM p and stage its retained peaks.
 // cpp/ModifiedPeptide.cpp:24-57 (initializeResidues), :59-79 (applyAuxMods).
@@ -228,6 +231,27 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
     info.Z = b.max_charge[p];
     int S = 0;
     __syncwarp();
+    // the retained peaks and the spectrum's m/z cell index travel global -> shared asynchronously while
+    // the residue tables are built (K1 stores the peaks in the staged {mz, rank} form)
+    bool staged = false;
+    if (want_peaks) {
+        const int sp = b.psm_spec[p];
+        const int64_t off = b.spec_off[sp] - b.spec_base;
+        const int R = b.rcount[sp];
+        const float2 head = b.chead[sp];
+        info.R = R;
+        info.gp = b.rpk + off;
+        info.cell_base = head.x;
+        info.cell_inv = head.y;
+        staged = R <= PA_RCAP && head.y != 0.f;
+        if (staged) {
+            for (int i = lane; i < R; i += 32) pa_cp_async8(&sm->pk[i], b.rpk + off + i);
+            // (pa_cell is monotone in x, so every peak before cell[pa_cell(lo)] is <= lo)
+            pa_cp_async8((unsigned long long*)sm->cell + lane, (const unsigned long long*)(b.ctab + (size_t)sp * PA_NCELL) + lane);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            if (lane == 0) sm->pk[R] = make_float2(__int_as_float(0x7f800000), __int_as_float(255));   // sentinel
+        }
+    }
     for (int base = 0; base < L; base += 32) {
         int i = base + lane;
         bool site = false;
@@ -276,28 +300,11 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
     }
     __syncwarp();
     if (want_peaks) {
-        int sp = b.psm_spec[p];
-        int64_t off = b.spec_off[sp] - b.spec_base;
-        int R = b.rcount[sp];
-        info.R = R;
-        const float2 head = b.chead[sp];
-        if (R <= PA_RCAP && head.y != 0.f) {
-            for (int i = lane; i <= R; i += 32)
-                sm->pk[i] = (i < R) ? make_float2(b.rmz[off + i], __int_as_float((int)b.rrank[off + i]))
-                                    : make_float2(__int_as_float(0x7f800000), __int_as_float(255));
-            // the m/z cell index K1 built for this spectrum (pa_cell is monotone in x, so every
-            // peak before cell[pa_cell(lo)] is <= lo)
-            const unsigned long long* src = (const unsigned long long*)(b.ctab + (size_t)sp * PA_NCELL);
-            ((unsigned long long*)sm->cell)[lane] = src[lane];
-            info.pm = b.rmz + off;
-            info.pr = b.rrank + off;
+        if (staged) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             info.pk = sm->pk;
             info.cell = sm->cell;
-            info.cell_base = head.x;
-            info.cell_inv = head.y;
         } else {
-            info.pm = b.rmz + off;
-            info.pr = b.rrank + off;
             info.pk = nullptr;
             info.cell = nullptr;
             info.cell_base = 0.f;
@@ -328,20 +335,19 @@ __device__ __forceinline__ int pa_match_rank(const PsmInfo& info, float f, float
         }
         return best;
     }
-    const float* pm = info.pm;
-    const uint8_t* pr = info.pr;
+    const float2* gp = info.gp;
     const int R = info.R;
     int a = 0;
-    int n = R;                          // first index with pm > lo
+    int n = R;                          // first index with mz > lo
     while (n > 0) {
         int h = n >> 1;
-        if (!(pm[a + h] > lo)) { a += h + 1; n -= h + 1; } else n = h;
+        if (!(gp[a + h].x > lo)) { a += h + 1; n -= h + 1; } else n = h;
     }
     for (; a < R; a++) {
-        float p = pm[a];
-        if (!(p < hi)) break;
-        if (err_gt_half && !((double)f >= (double)p - .5)) continue;
-        int r = pr[a];
+        const float2 e = gp[a];
+        if (!(e.x < hi)) break;
+        if (err_gt_half && !((double)f >= (double)e.x - .5)) continue;
+        const int r = __float_as_int(e.y);
         best = r < best ? r : best;
     }
     return best;

@@ -66,7 +66,8 @@ struct PaBinArgs {
     const double* inten;
     int64_t peak_base;       // spec_off values are relative to this
     int64_t n_spec;
-    float* rmz;
+    float2* rpk;             // retained peaks {(float)mz, rank as int bits}, m/z ascending, at the input offsets
+    float* rmz;              // probe outputs (null on the scoring path): the same as separate arrays
     uint8_t* rrank;
     int32_t* rcount;
     uint8_t* ctab;           // per spectrum PA_NCELL bytes (m/z cell index of the retained peaks)
@@ -94,11 +95,6 @@ struct PaBinArgs {
 #define PA_K1_UNROLL 2       // interior groups of the rank walk per trip (bins hold ~5 groups: deeper unrolling only adds remainders)
 #endif
 #define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 17 + PA_NBIN_SMEM * 4 + PA_NCELL)
-
-__device__ __forceinline__ void pa_cp_async8(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
 
 __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -313,15 +309,15 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 const unsigned below = (1u << lane) - 1u;       // every lane has read its own entries by now
                 int pos = out + __popc(bal0 & below) + __popc(bal1 & below);
                 if (keep0) {
-                    a.rmz[off + pos] = mz0;
-                    a.rrank[off + pos] = (uint8_t)cnt0;
+                    a.rpk[off + pos] = make_float2(mz0, __int_as_float(cnt0));
+                    if (a.rmz) { a.rmz[off + pos] = mz0; a.rrank[off + pos] = (uint8_t)cnt0; }
                     if (a.rindex) { a.rindex[off + pos] = i0; a.rbin[off + pos] = bq0; }
                     s_mzf[pos] = mz0;               // pos <= i0: only entries this or earlier rounds own
                     pos++;
                 }
                 if (keep1) {
-                    a.rmz[off + pos] = mz1;
-                    a.rrank[off + pos] = (uint8_t)cnt1;
+                    a.rpk[off + pos] = make_float2(mz1, __int_as_float(cnt1));
+                    if (a.rmz) { a.rmz[off + pos] = mz1; a.rrank[off + pos] = (uint8_t)cnt1; }
                     if (a.rindex) { a.rindex[off + pos] = i1; a.rbin[off + pos] = bq1; }
                     s_mzf[pos] = mz1;
                 }
@@ -412,8 +408,8 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                         float fj = __double2float_rn(a.mz[off + j]);
                         pos += (fj < fi) || (fj == fi && j < i);
                     }
-                    a.rmz[off + pos] = fi;
-                    a.rrank[off + pos] = a.g_tmp[off + i];
+                    a.rpk[off + pos] = make_float2(fi, __int_as_float((int)a.g_tmp[off + i]));
+                    if (a.rmz) { a.rmz[off + pos] = fi; a.rrank[off + pos] = a.g_tmp[off + i]; }
                     if (a.rindex) { a.rindex[off + pos] = i; a.rbin[off + pos] = a.g_bin[off + i]; }
                 }
                 total += __popc(__ballot_sync(PA_FULL, keep));
@@ -1323,7 +1319,7 @@ __device__ __forceinline__ float asc_res(const PaCfg& cfg, const AscPep& q, int 
     return m;
 }
 
-__device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int R, const uint8_t* ctab, float cbase,
+__device__ __forceinline__ int asc_match(const float2* pp, int R, const uint8_t* ctab, float cbase,
                                          float cinv, float f, float err, int err_gt_half) {
     const float lo = __fsub_rn(f, err), hi = __fadd_rn(f, err);
     int a;
@@ -1334,23 +1330,23 @@ __device__ __forceinline__ int asc_match(const float* pm, const uint8_t* pr, int
         int n = R;
         while (n > 0) {
             int h = n >> 1;
-            if (!(__ldg(pm + a + h) > lo)) { a += h + 1; n -= h + 1; } else n = h;
+            if (!(__ldg(pp + a + h).x > lo)) { a += h + 1; n -= h + 1; } else n = h;
         }
     }
     int best = 255;
     for (; a < R; a++) {
-        const float p = __ldg(pm + a);
-        if (!(p < hi)) break;
-        if (!(p > lo)) continue;
-        if (err_gt_half && !((double)f >= (double)p - .5)) continue;
-        const int r = __ldg(pr + a);
+        const float2 e = __ldg(pp + a);           // {mz, rank bits}: one load per candidate
+        if (!(e.x < hi)) break;
+        if (!(e.x > lo)) continue;
+        if (err_gt_half && !((double)f >= (double)e.x - .5)) continue;
+        const int r = __float_as_int(e.y);
         best = r < best ? r : best;
     }
     return best;
 }
 
 struct AscPeaks {
-    const float* pm; const uint8_t* pr; int R; const uint8_t* ctab; float cbase, cinv;
+    const float2* pp; int R; const uint8_t* ctab; float cbase, cinv;
 };
 
 #define ASC_BLOCK 128
@@ -1358,7 +1354,7 @@ struct AscPeaks {
 // a survivor of the merge: one trial of its list, a hit when its matched peak is ranked within `depth`
 __device__ __forceinline__ void asc_survivor(const PaCfg& cfg, const AscPeaks& pk, int depth, float v, bool from_a,
                                              int& hitsA, int& trialsA, int& hitsB, int& trialsB) {
-    const int hit = asc_match(pk.pm, pk.pr, pk.R, pk.ctab, pk.cbase, pk.cinv, v, cfg.err, cfg.err_gt_half) <= depth;
+    const int hit = asc_match(pk.pp, pk.R, pk.ctab, pk.cbase, pk.cinv, v, cfg.err, cfg.err_gt_half) <= depth;
     if (from_a) { trialsA++; hitsA += hit; } else { trialsB++; hitsB += hit; }
 }
 
@@ -1671,7 +1667,7 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
     const int sp = b.psm_spec[p];
     const int64_t off = b.spec_off[sp] - b.spec_base;
     AscPeaks pk;
-    pk.pm = b.rmz + off; pk.pr = b.rrank + off; pk.R = b.rcount[sp];
+    pk.pp = b.rpk + off; pk.R = b.rcount[sp];
     pk.ctab = b.ctab + (size_t)sp * PA_NCELL;
     { const float2 chead = b.chead[sp]; pk.cbase = chead.x; pk.cinv = chead.y; }
 

@@ -56,7 +56,7 @@ struct Slot {                // per-stream working set
     // staged inputs
     DevBuf spec_off, mz, inten, psm_spec, pep_off, pep, n_mod, max_charge, aux_off, aux_pos, aux_mass, mod_off;
     // K1
-    DevBuf rmz, rrank, rcount, ctab, chead, g_bin, g_tmp;
+    DevBuf rpk, rmz, rrank, rcount, ctab, chead, g_bin, g_tmp;
     // plan
     DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
     // K2/K3
@@ -68,7 +68,7 @@ struct Slot {                // per-stream working set
     cudaEvent_t ev_plan = nullptr;
     void release() {
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
-                         &aux_mass, &mod_off, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
+                         &aux_mass, &mod_off, &rpk, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
                          &iso_w, &g_sort, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
@@ -645,8 +645,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     b.spec_base = 0; b.n_spec = r.s1;   // spectrum indices stay absolute (views are pre-offset)
 
     // K1 buffers, indexed by absolute peak / spectrum index
-    CK(sl.rmz.ensure((size_t)std::max<int64_t>(npk, 1) * sizeof(float)));
-    CK(sl.rrank.ensure((size_t)std::max<int64_t>(npk, 1)));
+    CK(sl.rpk.ensure((size_t)std::max<int64_t>(npk, 1) * sizeof(float2)));
     CK(sl.g_bin.ensure((size_t)std::max<int64_t>(npk, 1) * sizeof(int32_t)));
     CK(sl.g_tmp.ensure((size_t)std::max<int64_t>(npk, 1)));
     CK(sl.rcount.ensure((size_t)std::max<int64_t>(ns, 1) * sizeof(int32_t)));
@@ -655,7 +654,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     PaBinArgs ba;
     ba.spec_off = b.spec_off + r.s0;          // kernel indexes spectra 0..ns-1
     ba.mz = v_mz; ba.inten = v_int; ba.peak_base = 0; ba.n_spec = ns;
-    ba.rmz = sl.rmz.as<float>() - peak_lo; ba.rrank = sl.rrank.as<uint8_t>() - peak_lo;
+    ba.rpk = sl.rpk.as<float2>() - peak_lo; ba.rmz = nullptr; ba.rrank = nullptr;
     ba.g_bin = sl.g_bin.as<int32_t>() - peak_lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - peak_lo;
     ba.rcount = sl.rcount.as<int32_t>();
     ba.ctab = sl.ctab.as<uint8_t>(); ba.chead = sl.chead.as<float2>();
@@ -674,7 +673,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
         s->ctr.kernel_launches++; s->ctr.launches_bin++;
     }
     CK(cudaEventRecord(cs.e_bin1, st));
-    b.rmz = ba.rmz; b.rrank = ba.rrank; b.rcount = sl.rcount.as<int32_t>() - r.s0;
+    b.rpk = ba.rpk; b.rcount = sl.rcount.as<int32_t>() - r.s0;
     b.ctab = sl.ctab.as<uint8_t>() - (size_t)r.s0 * PA_NCELL; b.chead = sl.chead.as<float2>() - r.s0;
 
     // plan
@@ -1131,7 +1130,7 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     CK(stage_in(sl.spec_off, spec_off, false, 0, n_spec + 1, st, &v_off, &dummy));
     CK(stage_in(sl.mz, mz, false, lo, npk, st, &v_mz, &dummy));
     CK(stage_in(sl.inten, inten, false, lo, npk, st, &v_int, &dummy));
-    CK(sl.rmz.ensure(npk1 * 4)); CK(sl.rrank.ensure(npk1));
+    CK(sl.rpk.ensure(npk1 * sizeof(float2))); CK(sl.rmz.ensure(npk1 * 4)); CK(sl.rrank.ensure(npk1));
     CK(sl.g_bin.ensure(npk1 * 4)); CK(sl.g_tmp.ensure(npk1));
     CK(sl.rcount.ensure((size_t)n_spec * 4));
     CK(sl.ctab.ensure((size_t)n_spec * PA_NCELL)); CK(sl.chead.ensure((size_t)n_spec * sizeof(float2)));
@@ -1142,7 +1141,7 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     for (int64_t q = 0; q < n_spec; q++) m = std::max<int64_t>(m, spec_off[q + 1] - spec_off[q]);
     PaBinArgs ba;
     ba.spec_off = v_off; ba.mz = v_mz; ba.inten = v_int; ba.peak_base = 0; ba.n_spec = n_spec;
-    ba.rmz = sl.rmz.as<float>() - lo; ba.rrank = sl.rrank.as<uint8_t>() - lo;
+    ba.rpk = sl.rpk.as<float2>() - lo; ba.rmz = sl.rmz.as<float>() - lo; ba.rrank = sl.rrank.as<uint8_t>() - lo;
     ba.g_bin = sl.g_bin.as<int32_t>() - lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - lo;
     ba.rcount = sl.rcount.as<int32_t>(); ba.bin_size = s->bin_size; ba.n_top = s->n_top;
     ba.ctab = sl.ctab.as<uint8_t>(); ba.chead = sl.chead.as<float2>();
