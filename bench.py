@@ -175,6 +175,48 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_near_gpu(index):
+    """Best effort: run this rank (and the pinned buffers it allocates: first touch) on the CPUs of the NUMA
+    node its GPU hangs off, so that the end-to-end leg does not cross the socket interconnect.  Returns a
+    short description for the JSON line; does nothing when the topology is not visible."""
+    try:
+        r = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                           capture_output=True, text=True, timeout=20)
+        bus = r.stdout.strip().splitlines()[0].strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return "numa node not reported"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return "numa node %d has no usable cpus" % node
+        os.sched_setaffinity(0, cpus)
+        return "bound to numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+
+
+def retained_peaks(batch, bin_size, n_top, n_sample=2000):
+    """Peaks K1 retains (<= n_top per bin), counted exactly on the first n_sample spectra and scaled to the batch."""
+    off = batch["spec_off"]
+    n_spec = off.size - 1
+    m = min(n_sample, n_spec)
+    kept = 0
+    for q in range(m):
+        mz = batch["mz"][off[q]:off[q + 1]]
+        if mz.size == 0:
+            continue
+        lo = np.float32(np.floor(mz.min() / 100.) * 100.)
+        bins = np.floor((mz - np.float64(lo)) / np.float64(np.float32(bin_size))).astype(np.int64)
+        kept += int(np.minimum(np.bincount(bins - bins.min()), n_top).sum())
+    return kept * n_spec // max(m, 1)
+
+
 def algorithmic_bytes(batch, res_mod_total):
     """16*P/h + L + 8*A + 24 in, 16 + 4*k + 4*sum|alt| out, summed over the batch
     (alt term bounded by one 8-byte mask per mod, which is what the ABI returns)"""
@@ -235,7 +277,8 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
-    procs = max(1, cores // world)
+    numa = bind_near_gpu(local) if world > 1 else "single rank: not bound"
+    procs = max(1, min(cores // world, len(os.sched_getaffinity(0))))
     t0 = time.time()
     batch = generate(args.workload, n_psm, args.seed + 1000 * rank, procs)   # before any CUDA call (fork)
     gen_s = time.time() - t0
@@ -334,11 +377,15 @@ def main():
                     "select": ctr_dev["launches_select"], "ascore": max(ctr_dev["launches_ascore"] // 2, 1)}[dom]
         peaks_n = int(batch["spec_off"][-1])
         # algorithmic bytes of each kernel's own stage per step (DESIGN.md section "kernels")
-        retained = 5 * min(peaks_n, 10 * 20 * (batch["spec_off"].size - 1))
-        alg = {"bin_topn": 16 * peaks_n + retained,
-               "count_score": retained + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 12 * n_psm + 24 * int(ctr_dev["n_isoforms"]),
-               "select": 4 * int(ctr_dev["n_isoforms"]) + 28 * n_psm + 20 * mod_total,
-               "ascore": retained + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 16 * mod_total + 4 * mod_total}
+        n_spec = batch["spec_off"].size - 1
+        hits = w["hits"]
+        # K1 writes, and K2 / K3b read, 8 B per retained peak plus the 256-cell index, its header and the count
+        retained = 8 * retained_peaks(batch, w["scorer"]["bin_size"], w["scorer"]["n_top"])
+        index = 268 * n_spec
+        alg = {"bin_topn": 16 * peaks_n + retained + index,
+               "count_score": (retained + index) * hits + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 12 * n_psm + 24 * int(ctr_dev["n_isoforms"]),
+               "select": 4 * int(ctr_dev["n_isoforms"]) + 28 * n_psm + int(batch["pep_off"][-1]) + 26 * mod_total,
+               "ascore": (retained + index) * hits + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 16 * mod_total + 4 * mod_total}
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per PSM at
         # 262144 PSMs/launch, profiles/traffic.json), scaled to this run's PSMs per launch
         traffic = None
@@ -387,6 +434,7 @@ def main():
             "kernel_ms_per_step": kern, "wall_ms_per_step": wall_dev_ms / args.steps,
             "isoforms_per_step": int(ctr_dev["n_isoforms"]), "fragment_lookups_per_step": int(ctr_dev["n_fragment_lookups"]),
             "host_and_device_paths_bit_identical": bool(same), "psms_not_scored": n_bad, "gen_seconds": gen_s,
+            "numa": numa,
         }
         if world == 1 and not args.no_cpu_baseline:
             # CPU reference on this box's host cores, in a fresh process (no fork after CUDA init)
