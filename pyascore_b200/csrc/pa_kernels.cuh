@@ -1742,8 +1742,14 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
 #ifndef PA_ASC_MINBLOCKS
 #define PA_ASC_MINBLOCKS 8
 #endif
+#ifndef PA_ASC4_MINBLOCKS
+#define PA_ASC4_MINBLOCKS 4
+#endif
+#ifndef PA_ASC12_MINBLOCKS
+#define PA_ASC12_MINBLOCKS 4
+#endif
 template <int NQ, int CLS>
-__global__ void __launch_bounds__(128, (NQ <= 2 ? PA_ASC_MINBLOCKS : 4)) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
+__global__ void __launch_bounds__(128, (NQ <= 2 ? PA_ASC_MINBLOCKS : (NQ <= 4 ? PA_ASC4_MINBLOCKS : PA_ASC12_MINBLOCKS))) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.work_count[CLS]) return;
     int64_t first = 0;                       // classes are contiguous in the sorted list

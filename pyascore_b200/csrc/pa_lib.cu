@@ -589,6 +589,52 @@ static cudaError_t copy_out(const DevBuf& buf, T* dst, bool on_dev, int64_t lo, 
     return cudaMemcpyAsync(dst + lo, buf.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st);
 }
 
+// ---- chunk boundaries of a device-resident batch --------------------------------------------------
+// Chunks a device-resident batch is cut into (the two streams alternate).  Measured on config 2 (1 M PSMs):
+// 1 chunk 91.5 M PSM/s, 2 chunks 94.1 M, 4 chunks 84.0 M, 8 chunks 70.2 M -- the persistent kernels of two
+// chunks cannot share an SM (registers / shared memory), so more chunks only add launches and tails.  One
+// chunk keeps the per-kernel event times free of overlap, which the roofline arithmetic relies on.
+#ifndef PA_DEV_CHUNKS
+#define PA_DEV_CHUNKS 1
+#endif
+#define PA_DEV_CHUNK_MIN 65536          // ... as long as each keeps at least this many PSMs
+#define PA_DEV_CHUNKS_MAX 16
+struct DevBounds {
+    int n;                              // boundaries 0..n (n = number of chunks)
+    int bad;                            // psm_spec decreasing or out of range somewhere
+    int max_peaks;                      // largest spectrum of the batch
+    int pad;
+    int64_t p[PA_DEV_CHUNKS_MAX + 1];       // first PSM of chunk c (p[n] = n_psm)
+    int64_t s0[PA_DEV_CHUNKS_MAX + 1];      // first spectrum chunk c references
+    int64_t s1[PA_DEV_CHUNKS_MAX + 1];      // one past the last spectrum chunk c-1 references
+    int64_t peak0[PA_DEV_CHUNKS_MAX + 1], peak1[PA_DEV_CHUNKS_MAX + 1];     // spec_off at s0 / s1
+    int64_t pep[PA_DEV_CHUNKS_MAX + 1], mod[PA_DEV_CHUNKS_MAX + 1];         // pep_off / mod_off at p
+};
+
+__global__ void k_dev_bounds(const int64_t* spec_off, const int32_t* psm_spec, const int32_t* pep_off,
+                             const int64_t* mod_off, int64_t n_psm, int64_t n_spec, int C, int64_t per, DevBounds* o) {
+    const int c = threadIdx.x;
+    if (c == 0) o->n = C;
+    if (c > C) return;
+    const int64_t p = (int64_t)c * per < n_psm ? (int64_t)c * per : n_psm;
+    int64_t s0 = p < n_psm ? (int64_t)psm_spec[p] : n_spec;
+    int64_t s1 = p > 0 ? (int64_t)psm_spec[p - 1] + 1 : 0;
+    s0 = s0 < 0 ? 0 : (s0 > n_spec ? n_spec : s0);
+    s1 = s1 < 0 ? 0 : (s1 > n_spec ? n_spec : s1);
+    o->p[c] = p; o->s0[c] = s0; o->s1[c] = s1;
+    o->peak0[c] = spec_off[s0]; o->peak1[c] = spec_off[s1];
+    o->pep[c] = pep_off[p]; o->mod[c] = mod_off[p];
+}
+
+__global__ void k_check_psm_spec(const int32_t* psm_spec, int64_t n_psm, int64_t n_spec, int* bad) {
+    bool b = false;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_psm; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = psm_spec[p];
+        b |= v < 0 || v >= n_spec || (p > 0 && v < psm_spec[p - 1]);
+    }
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicExch(bad, 1);
+}
+
 struct ChunkRange { int64_t p0, p1, s0, s1; };
 
 struct ChunkState {              // what the back half of a chunk needs from the front half
@@ -600,20 +646,17 @@ struct ChunkState {              // what the back half of a chunk needs from the
     uint64_t* o_sig; float* o_score; int64_t* o_niso; int32_t* o_nsites; float* o_asc; uint64_t* o_alt; int32_t* o_status;
 };
 
+struct ChunkEnds { int64_t peak_lo, peak_hi, pep_lo, pep_hi; };   // range ends of a device-resident chunk
+
 static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, const ChunkRange& r, int64_t mod_lo,
-                       int64_t mod_hi, int max_peaks, ChunkState& cs) {
+                       int64_t mod_hi, int max_peaks, ChunkState& cs, const ChunkEnds* ends_dev) {
     Slot& sl = s->slot[si];
     cudaStream_t st = sl.st;
     const int64_t np = r.p1 - r.p0, ns = r.s1 - r.s0;
     int64_t peak_lo, peak_hi, pep_lo, pep_hi, aux_lo = 0, aux_hi = 0;
     if (in_dev) {
-        // offsets live on the device: read the four range ends we need
-        int64_t ends[2]; int32_t pe[2];
-        CK(cudaMemcpy(&ends[0], in->spec_off + r.s0, sizeof(int64_t), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(&ends[1], in->spec_off + r.s1, sizeof(int64_t), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(&pe[0], in->pep_off + r.p0, sizeof(int32_t), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(&pe[1], in->pep_off + r.p1, sizeof(int32_t), cudaMemcpyDeviceToHost));
-        peak_lo = ends[0]; peak_hi = ends[1]; pep_lo = pe[0]; pep_hi = pe[1];
+        // offsets live on the device: pa_score_batch fetched the range ends of every chunk in one go
+        peak_lo = ends_dev->peak_lo; peak_hi = ends_dev->peak_hi; pep_lo = ends_dev->pep_lo; pep_hi = ends_dev->pep_hi;
     } else {
         peak_lo = in->spec_off[r.s0]; peak_hi = in->spec_off[r.s1];
         pep_lo = in->pep_off[r.p0]; pep_hi = in->pep_off[r.p1];
@@ -915,7 +958,47 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
     std::vector<ChunkRange> chunks;
     std::vector<int> chunk_maxp;
     std::vector<int64_t> mod_lo, mod_hi;
-    if (in_dev || keep) {
+    std::vector<ChunkEnds> ends_dev;
+    int dev_max_peaks = 512;
+    if (in_dev) {
+        // Device-resident batch: PA_DEV_CHUNKS chunks that alternate between the two streams (see the note at
+        // PA_DEV_CHUNKS: one by default).  One small kernel gathers every range end the host needs, a second
+        // checks that psm_spec is non-decreasing (cutting on PSM indices relies on it), a third finds the
+        // largest spectrum: one device -> host copy instead of one per value.
+        int C = keep ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(PA_DEV_CHUNKS, in->n_psm / PA_DEV_CHUNK_MIN));
+        const int64_t per = (in->n_psm + C - 1) / C;
+        DevBuf& tb = s->slot[0].totals;
+        CK(tb.ensure(sizeof(PlanTotals) + sizeof(DevBounds)));
+        DevBounds* d_b = (DevBounds*)tb.p;
+        CK(cudaMemset(d_b, 0, sizeof(DevBounds)));
+        k_dev_bounds<<<1, 32>>>(in->spec_off, in->psm_spec, in->pep_off, in->mod_off, in->n_psm, in->n_spec, C, per, d_b);
+        k_check_psm_spec<<<(unsigned)std::min<int64_t>((in->n_psm + 255) / 256, 1184), 256>>>(in->psm_spec, in->n_psm, in->n_spec, &d_b->bad);
+        k_max_peaks<<<(unsigned)((in->n_spec + 255) / 256), 256>>>(in->spec_off, in->n_spec, &d_b->max_peaks);
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches += 3;
+        DevBounds hb;
+        CK(cudaMemcpy(&hb, d_b, sizeof(DevBounds), cudaMemcpyDeviceToHost));
+        dev_max_peaks = hb.max_peaks;
+        if (hb.bad) C = 1;                       // unordered PSM -> spectrum map: one chunk over everything
+        for (int c = 0; c < C; c++) {
+            const int a = (C == 1) ? 0 : c, z = (C == 1) ? hb.n : c + 1;       // boundary indices
+            ChunkRange r = {hb.p[a], hb.p[z], hb.bad ? 0 : hb.s0[a], hb.bad ? in->n_spec : hb.s1[z]};
+            if (r.p1 <= r.p0) continue;
+            chunks.push_back(r);
+            ChunkEnds e;
+            if (hb.bad) {
+                int64_t pk[2]; int32_t pe[2];
+                CK(cudaMemcpy(&pk[0], in->spec_off, 8, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&pk[1], in->spec_off + in->n_spec, 8, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&pe[0], in->pep_off, 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&pe[1], in->pep_off + in->n_psm, 4, cudaMemcpyDeviceToHost));
+                e = {pk[0], pk[1], pe[0], pe[1]};
+            } else e = {hb.peak0[a], hb.peak1[z], hb.pep[a], hb.pep[z]};
+            ends_dev.push_back(e);
+            mod_lo.push_back(hb.mod[a]); mod_hi.push_back(hb.mod[z]);
+            chunk_maxp.push_back(dev_max_peaks);
+        }
+    } else if (keep) {
         chunks.push_back({0, in->n_psm, 0, in->n_spec});
     } else {
         bool mono = true;
@@ -936,41 +1019,25 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
             }
         }
     }
-    for (auto& c : chunks) {
-        int mp = 512;
-        if (!in_dev) {
+    if (!in_dev)
+        for (auto& c : chunks) {
             int64_t m = 0;
             for (int64_t q = c.s0; q < c.s1; q++) m = std::max<int64_t>(m, in->spec_off[q + 1] - in->spec_off[q]);
-            mp = (int)std::min<int64_t>(m, 1 << 20);
+            chunk_maxp.push_back((int)std::min<int64_t>(m, 1 << 20));
             mod_lo.push_back(in->mod_off[c.p0]); mod_hi.push_back(in->mod_off[c.p1]);
-        } else {
-            int64_t e[2];
-            CK(cudaMemcpy(&e[0], in->mod_off + c.p0, 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(&e[1], in->mod_off + c.p1, 8, cudaMemcpyDeviceToHost));
-            mod_lo.push_back(e[0]); mod_hi.push_back(e[1]);
-            // spectrum sizes live on the device: reduce the largest one there
-            CK(s->slot[0].totals.ensure(sizeof(PlanTotals)));
-            int* d_max = (int*)s->slot[0].totals.p;
-            CK(cudaMemset(d_max, 0, sizeof(int)));
-            k_max_peaks<<<(unsigned)((c.s1 - c.s0 + 255) / 256), 256>>>(in->spec_off + c.s0, c.s1 - c.s0, d_max);
-            CK(cudaGetLastError());
-            CK(cudaMemcpy(&mp, d_max, sizeof(int), cudaMemcpyDeviceToHost));
-            s->ctr.kernel_launches++;
         }
-        chunk_maxp.push_back(mp);
-    }
 
     // ---- two-slot software pipeline ----
     std::vector<ChunkState> cs(chunks.size());
     cudaEvent_t e_all0 = next_event(s), e_all1 = next_event(s);
     CK(cudaEventRecord(e_all0, s->slot[0].st));
-    rc = chunk_front(s, 0, in, in_dev, chunks[0], mod_lo[0], mod_hi[0], chunk_maxp[0], cs[0]);
+    rc = chunk_front(s, 0, in, in_dev, chunks[0], mod_lo[0], mod_hi[0], chunk_maxp[0], cs[0], in_dev ? &ends_dev[0] : nullptr);
     if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
     for (size_t c = 0; c < chunks.size(); c++) {
         if (c + 1 < chunks.size()) {
             // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
             rc = chunk_front(s, (int)((c + 1) & 1), in, in_dev, chunks[c + 1], mod_lo[c + 1], mod_hi[c + 1],
-                             chunk_maxp[c + 1], cs[c + 1]);
+                             chunk_maxp[c + 1], cs[c + 1], in_dev ? &ends_dev[c + 1] : nullptr);
             if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
         }
         rc = chunk_back(s, (int)(c & 1), out, out_dev, cs[c], keep);
