@@ -167,7 +167,7 @@ struct PsmSmem {
     float res[PA_LMAX][2];        // residue mass: [i][0] plain, [i][1] with the variable mod
     uint8_t nlidx[PA_LMAX][2];    // neutral-loss index per state (0 = none)
     uint8_t site_pos[64];         // residue index of site j
-    float2 pk[PA_RCAP + 1];       // retained peaks {(float)mz ascending, rank as int bits}; pk[R] = {+inf, 255}
+    float2 pk[PA_RCAP + 2];       // retained peaks {(float)mz ascending, rank as int bits}; pk[R] = {+inf, 255}, pk[R + 1] readable
     alignas(8) uint8_t cell[PA_NCELL];  // cell[c] = index of the first peak whose cell is >= c
 };
 
@@ -325,13 +325,18 @@ __device__ __forceinline__ int pa_match_rank(const PsmInfo& info, float f, float
         // staged peaks: every peak before cell[pa_cell(lo)] is <= lo; peaks <= lo inside the cell
         // are passed over by the same loop (they are < hi), and the +inf sentinel at pk[R] ends it
         const float2* pk = info.pk + info.cell[pa_cell(lo, info.cell_base, info.cell_inv)];
-        for (;; pk++) {
-            const float2 e = *pk;
+        // the first two candidates are fetched together (most scans end on the second): pk[R + 1] is readable
+        float2 e = pk[0], e_next = pk[1];
+        for (;;) {
             if (!(e.x < hi)) break;
             if (e.x > lo && !(err_gt_half && !((double)f >= (double)e.x - .5))) {
                 const int r = __float_as_int(e.y);
                 best = r < best ? r : best;
             }
+            pk++;
+            e = e_next;
+            if (!(e.x < hi)) break;      // (tested before the next fetch: the entry after the +inf sentinel is never read)
+            e_next = pk[1];
         }
         return best;
     }

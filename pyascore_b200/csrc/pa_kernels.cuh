@@ -1334,13 +1334,21 @@ __device__ __forceinline__ int asc_match(const float2* pp, int R, const uint8_t*
         }
     }
     int best = 255;
-    for (; a < R; a++) {
-        const float2 e = __ldg(pp + a);           // {mz, rank bits}: one load per candidate
-        if (!(e.x < hi)) break;
-        if (!(e.x > lo)) continue;
-        if (err_gt_half && !((double)f >= (double)e.x - .5)) continue;
-        const int r = __float_as_int(e.y);
-        best = r < best ? r : best;
+    if (a < R) {
+        // {mz, rank bits}: one load per candidate, the first two in flight together (most scans end on the second)
+        float2 e = __ldg(pp + a);
+        float2 e_next = __ldg(pp + (a + 1 < R ? a + 1 : R - 1));
+        for (;;) {
+            if (!(e.x < hi)) break;
+            if (e.x > lo && !(err_gt_half && !((double)f >= (double)e.x - .5))) {
+                const int r = __float_as_int(e.y);
+                best = r < best ? r : best;
+            }
+            if (++a >= R) break;
+            e = e_next;
+            if (!(e.x < hi)) break;
+            e_next = __ldg(pp + (a + 1 < R ? a + 1 : R - 1));
+        }
     }
     return best;
 }
@@ -1742,6 +1750,9 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
 #ifndef PA_ASC_MINBLOCKS
 #define PA_ASC_MINBLOCKS 8
 #endif
+#ifndef PA_ASC2_MINBLOCKS
+#define PA_ASC2_MINBLOCKS 8
+#endif
 #ifndef PA_ASC4_MINBLOCKS
 #define PA_ASC4_MINBLOCKS 4
 #endif
@@ -1749,7 +1760,7 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
 #define PA_ASC12_MINBLOCKS 4
 #endif
 template <int NQ, int CLS>
-__global__ void __launch_bounds__(128, (NQ <= 2 ? PA_ASC_MINBLOCKS : (NQ <= 4 ? PA_ASC4_MINBLOCKS : PA_ASC12_MINBLOCKS))) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
+__global__ void __launch_bounds__(128, (NQ <= 1 ? PA_ASC_MINBLOCKS : (NQ <= 2 ? PA_ASC2_MINBLOCKS : (NQ <= 4 ? PA_ASC4_MINBLOCKS : PA_ASC12_MINBLOCKS)))) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.work_count[CLS]) return;
     int64_t first = 0;                       // classes are contiguous in the sorted list
