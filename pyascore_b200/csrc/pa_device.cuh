@@ -25,6 +25,7 @@ struct PaCfg {
     int has_nl;                      // any neutral loss configured
     uint8_t nl_upper[26], nl_lower[26];  // 0 = none, else 1-based index of the distinct loss mass
     float res_mass[26];              // cpp/Types.h:7-30; NaN = unknown letter
+    uint32_t known_letters;          // bit (c-'A') set: res_mass[c] is a number (register test instead of a gather)
     float weights[PA_N_TOP];         // cpp/Ascore.cpp:15-19
     int err_gt_half;                 // mz_error > 0.5: the lower_bound(mz - .5) clause can bind
     int nvar_cap;                    // max neutral-loss variants per residue for this scorer

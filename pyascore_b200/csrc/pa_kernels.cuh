@@ -446,49 +446,62 @@ struct PaPlanOut {
 };
 
 __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n_psm, PaPlanOut o) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_psm) return;
-    const int off = b.pep_off[p];
-    const int L = b.pep_off[p + 1] - off;
-    const int k = b.n_mod[p], Z = b.max_charge[p];
-    const int sp = b.psm_spec[p];
-    int status = PA_PSM_OK, S = 0;
-    if (sp < 0 || sp >= b.n_spec || k < 0 || Z < 1 || L < 1) status = PA_PSM_BAD_INDEX;  // Z == 0 crashes the reference
-    else if (L > PA_MAX_PEPTIDE) status = PA_PSM_TOO_LONG;
-    else {
-        for (int i = 0; i < L; i++) {
-            int c = (int)b.pep[off + i] - 'A';
-            if (c < 0 || c >= 26 || isnan(cfg.res_mass[c])) { status = PA_PSM_BAD_RESIDUE; break; }
-            bool site = ((cfg.mod_letters >> c) & 1u) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == L - 1);
-            S += site;
-        }
-        if (status == PA_PSM_OK && b.aux_off != nullptr)
-            for (int a = b.aux_off[p]; a < b.aux_off[p + 1]; a++)
-                if (b.aux_pos[a] > (uint32_t)L) status = PA_PSM_BAD_AUX;
-        if (status == PA_PSM_OK && S > PA_MAX_SITES) status = PA_PSM_TOO_MANY_SITES;
-        if (status == PA_PSM_OK && b.rcount[sp] <= 0) status = PA_PSM_EMPTY_SPECTRUM;
-    }
-    int64_t I = 0;
-    if (status == PA_PSM_OK) {
-        long long per_type = (long long)(L > 1 ? L - 1 : 1) * cfg.nvar_cap * Z;
-        long long nf = per_type * cfg.n_types;
-        if (nf > PA_MAX_FRAGMENTS) status = PA_PSM_TOO_MANY_FRAGMENTS;
+    // chunk-wide maxima and the (S,k) combinations seen are collected per block in shared memory and
+    // flushed once: a global atomic per PSM and field would queue up on four addresses
+    __shared__ unsigned long long s_combo[64];
+    __shared__ int s_max[3];
+    if (threadIdx.x < 64) s_combo[threadIdx.x] = 0ull;
+    if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_psm) {
+        const int off = b.pep_off[p];
+        const int L = b.pep_off[p + 1] - off;
+        const int k = b.n_mod[p], Z = b.max_charge[p];
+        const int sp = b.psm_spec[p];
+        int status = PA_PSM_OK, S = 0;
+        if (sp < 0 || sp >= b.n_spec || k < 0 || Z < 1 || L < 1) status = PA_PSM_BAD_INDEX;  // Z == 0 crashes the reference
+        else if (L > PA_MAX_PEPTIDE) status = PA_PSM_TOO_LONG;
         else {
-            uint32_t c = (k <= S) ? cfg.binom[S * 64 + k] : 0u;
-            if ((long long)c > PA_MAX_ISOFORMS) status = PA_PSM_TOO_MANY_ISOFORMS;
+            for (int i = 0; i < L; i++) {
+                const int c = (int)b.pep[off + i] - 'A';
+                if (c < 0 || c >= 26 || !((cfg.known_letters >> c) & 1u)) { status = PA_PSM_BAD_RESIDUE; break; }
+                const bool site = ((cfg.mod_letters >> c) & 1u) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == L - 1);
+                S += site;
+            }
+            if (status == PA_PSM_OK && b.aux_off != nullptr)
+                for (int a = b.aux_off[p]; a < b.aux_off[p + 1]; a++)
+                    if (b.aux_pos[a] > (uint32_t)L) status = PA_PSM_BAD_AUX;
+            if (status == PA_PSM_OK && S > PA_MAX_SITES) status = PA_PSM_TOO_MANY_SITES;
+            if (status == PA_PSM_OK && b.rcount[sp] <= 0) status = PA_PSM_EMPTY_SPECTRUM;
+        }
+        int64_t I = 0;
+        if (status == PA_PSM_OK) {
+            long long per_type = (long long)(L > 1 ? L - 1 : 1) * cfg.nvar_cap * Z;
+            long long nf = per_type * cfg.n_types;
+            if (nf > PA_MAX_FRAGMENTS) status = PA_PSM_TOO_MANY_FRAGMENTS;
             else {
-                I = c;
-                atomicMax(o.max_frag, (int)nf);
-                atomicMax(o.max_list, (int)per_type);
-                atomicMax(o.max_len, L);
-                if (I > 1) atomicOr(&o.combo_bits[S], 1ull << k);
+                uint32_t c = (k <= S) ? cfg.binom[S * 64 + k] : 0u;
+                if ((long long)c > PA_MAX_ISOFORMS) status = PA_PSM_TOO_MANY_ISOFORMS;
+                else {
+                    I = c;
+                    atomicMax(&s_max[0], (int)nf);
+                    atomicMax(&s_max[1], (int)per_type);
+                    atomicMax(&s_max[2], L);
+                    if (I > 1) atomicOr(&s_combo[S], 1ull << k);
+                }
             }
         }
+        o.psm_S[p] = S;
+        o.psm_status[p] = status;
+        o.psm_I[p] = I;
+        o.psm_units[p] = (int32_t)((I + PA_UNIT - 1) / PA_UNIT);
     }
-    o.psm_S[p] = S;
-    o.psm_status[p] = status;
-    o.psm_I[p] = I;
-    o.psm_units[p] = (int32_t)((I + PA_UNIT - 1) / PA_UNIT);
+    __syncthreads();
+    if (threadIdx.x < 64 && s_combo[threadIdx.x]) atomicOr(&o.combo_bits[threadIdx.x], s_combo[threadIdx.x]);
+    if (threadIdx.x == 64 && s_max[0] > 0) atomicMax(o.max_frag, s_max[0]);
+    if (threadIdx.x == 65 && s_max[1] > 0) atomicMax(o.max_list, s_max[1]);
+    if (threadIdx.x == 66 && s_max[2] > 0) atomicMax(o.max_len, s_max[2]);
 }
 
 __global__ void k_expand_units(int64_t n_psm, const int32_t* unit_off, int32_t* unit_psm) {

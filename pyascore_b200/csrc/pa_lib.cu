@@ -270,7 +270,11 @@ static int refresh_config(pa_scorer* s) {
     c.n_types = (int)s->frag_types.size();
     memset(c.types, 0, sizeof(c.types));
     memcpy(c.types, s->frag_types.data(), s->frag_types.size());
-    for (int i = 0; i < 26; i++) c.res_mass[i] = residue_mass_host((char)('A' + i));
+    c.known_letters = 0;
+    for (int i = 0; i < 26; i++) {
+        c.res_mass[i] = residue_mass_host((char)('A' + i));
+        if (!std::isnan(c.res_mass[i])) c.known_letters |= 1u << i;
+    }
     // cpp/Ascore.cpp:15-19
     const float w0[PA_N_TOP] = {0.5f, 0.75f, 1.0f, 1.0f, 1.0f, 1.0f, 0.75f, 0.5f, 0.25f, 0.25f};
     double sum = 0.;
