@@ -556,7 +556,7 @@ __device__ __forceinline__ int pa_emit_step(const PaCfg& cfg, const PsmInfo& inf
                                             unsigned long long& chi) {
     const int Z = info.Z;
     int nv = 1;
-    if (HAS_NL) nv = cfg.nl_nvar[nls];
+    if (HAS_NL) nv = ((const uint8_t*)(s_nl + 256 * 16))[nls];       // variant counts sit behind the sums in shared memory
     // L == 1: the walk starts on the last residue and the reference's end test lets all but
     // the last neutral-loss variant through (cpp/ModifiedPeptide.cpp:516-524)
     if (info.L == 1) nv -= 1;
@@ -668,13 +668,16 @@ template <bool HAS_NL, bool PAIR, bool EGH>
 __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg, PaBatchDev b, PaCountArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ ulonglong2 s_lut[16];
-    __shared__ float s_nl[HAS_NL ? 256 * 16 : 1];
+    __shared__ float s_nl[HAS_NL ? 256 * 16 + 64 : 1];   // neutral-loss variant sums [256][16] + variant counts u8[256]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     if (threadIdx.x < 16) {
         const int r = threadIdx.x;
         s_lut[r] = make_ulonglong2(r < 5 ? 1ull << (12 * r) : 0ull, (r >= 5 && r < 10) ? 1ull << (12 * (r - 5)) : 0ull);
     }
-    if (HAS_NL) for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) s_nl[i] = cfg.nl_sums[i];
+    if (HAS_NL) {
+        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) s_nl[i] = cfg.nl_sums[i];
+        if (threadIdx.x < 256) ((uint8_t*)(s_nl + 256 * 16))[threadIdx.x] = cfg.nl_nvar[threadIdx.x];
+    }
     __syncthreads();
     PsmSmem* sm = (PsmSmem*)smem_raw + wib;
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
