@@ -798,6 +798,9 @@ struct PaSelArgs {
     int* work_count;             // [4] entries per stream class (k_ascore)
     const int32_t* order;        // optional visiting order of the PSMs (null = input order)
     unsigned long long* next_psm;    // work cursor (zeroed before the launch)
+    int32_t* rest_list;              // PSMs k_select_thread leaves to k_select (large isoform sets, tied top scores)
+    int* rest_count;
+    const int* n_psm_dev;            // k_select: number of PSMs to visit when it is only known on the device (else null)
     int grab;                        // PSMs per visit to the cursor: 1 .. PA_SEL_GRAB; negative: no reservation ahead
 };
 #ifndef PA_SEL_GRAB
@@ -1090,6 +1093,148 @@ __device__ __forceinline__ void pa_depth_scores(const PaCfg& cfg, unsigned long 
     for (int d = 0; d < PA_N_TOP; d++) sc[d] = __ldg(cfg.T + pa_tab_index(n, pa_cum_get(lo, hi, d), d));
 }
 
+// position of the n-th set bit (n counted from 0) of a 128-bit mask
+__device__ __forceinline__ int pa_nth_set(uint64_t lo, uint64_t hi, int n) {
+    const int c = __popcll(lo);
+    uint64_t x = lo;
+    int base = 0;
+    if (n >= c) { x = hi; n -= c; base = 64; }
+    for (int i = 0; i < n; i++) x &= x - 1;
+    return base + __ffsll((long long)x) - 1;
+}
+
+// K3a, common case: one THREAD per PSM.  A PSM of config-2 size has a dozen isoforms and a handful of
+// sites: a warp per PSM spends its instructions on reductions over mostly empty lanes.  A thread walks
+// the same steps serially (best isoform, per modified site the tied best competitors, Ascore-0 shortcut,
+// sort key of every Ascore entry).  PSMs whose best score is tied among more than 16 isoforms (the
+// reference's std::sort order decides, which takes the warp kernel's sort replay) or that have more than
+// PA_SEL_THREAD_MAX isoforms are left, untouched, to k_select through rest_list.
+#define PA_SEL_THREAD_MAX 512
+__global__ void __launch_bounds__(128) k_select_thread(PaCfg cfg, PaBatchDev b, PaSelArgs a) {
+    __shared__ int s_cls[4];
+    if (threadIdx.x < 4) s_cls[threadIdx.x] = 0;
+    __syncthreads();
+    const float INF = __int_as_float(0x7f800000);
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.n_psm) {
+        const int status = a.psm_status[p];
+        const int k = b.n_mod[p];
+        const int64_t mo = a.mod_off[p];
+        const int S = a.psm_S[p];
+        const int64_t ib = a.iso_off[p];
+        const int64_t I = a.iso_off[p + 1] - ib;
+        bool rest = false;
+        float wmax = -INF;
+        uint32_t best = 0xffffffffu;
+        const bool none = status != PA_PSM_OK || I == 0 || k >= S;
+        if (!none) {
+            if (I > PA_SEL_THREAD_MAX) rest = true;
+            else {
+                int ties = 0;
+                for (int64_t q = 0; q < I; q++) {
+                    const float w = a.iso.w[ib + q];
+                    if (w > wmax) { wmax = w; ties = 1; best = (uint32_t)q; }
+                    else if (w == wmax) { if (ties == 0) best = (uint32_t)q; ties++; }
+                }
+                if (ties > 1) {
+                    if (I > 16) rest = true;
+                    else {
+                        // std::sort on <= 16 elements is a stable insertion sort: the first maximal element
+                        // in hash-iteration order stays in front
+                        const uint32_t* perm = a.perm_pool + a.perm_off[S * 64 + k];
+                        for (int t = 0; t < (int)I; t++) {
+                            const uint32_t id = perm[t];
+                            if (a.iso.w[ib + id] == wmax) { best = id; break; }
+                        }
+                    }
+                }
+            }
+        }
+        if (rest) {
+            a.rest_list[atomicAdd(a.rest_count, 1)] = (int32_t)p;
+        } else {
+            if (a.psm_status_out) a.psm_status_out[p] = status;
+            if (a.n_iso) a.n_iso[p] = I;
+            if (a.n_sites) a.n_sites[p] = S;
+            if (none) {
+                // no isoform: best_sequence "" / best_score -1 (cpp/Ascore.cpp:273-295); k >= #sites is
+                // "unambiguous" (cpp/Ascore.cpp:38-51: ascores inf, no alternatives); errors report NaN
+                const bool ok = status == PA_PSM_OK;
+                const float fill = ok ? INF : __int_as_float(0x7fc00000);
+                uint64_t sig = 0; float sc = ok ? -1.f : fill;
+                if (ok && I > 0) { sig = (S >= 64) ? ~0ull : ((1ull << S) - 1ull); sc = a.iso.w[ib]; }
+                if (a.best_sig) a.best_sig[p] = sig;
+                if (a.best_score) a.best_score[p] = sc;
+                a.best_idx[p] = (ok && I > 0) ? 0u : 0xffffffffu;
+                for (int j = 0; j < k; j++) {
+                    if (a.ascores) a.ascores[mo + j] = fill;
+                    if (a.alt_sites) a.alt_sites[mo + j] = 0;
+                    a.mod_psm[mo + j - a.mod_lo] = -1;
+                    a.work_key[mo + j - a.mod_lo] = (uint16_t)PA_WORK_NONE;
+                    a.work_val[mo + j - a.mod_lo] = (int32_t)(mo + j - a.mod_lo);
+                }
+            } else {
+                const uint64_t best_bits = pa_unrank(cfg.binom, S, k, best);
+                const float wb = a.iso.w[ib + best];
+                if (a.best_sig) a.best_sig[p] = best_bits;
+                if (a.best_score) a.best_score[p] = wb;
+                a.best_idx[p] = best;
+                // residues that are sites, for the merge-length estimate (see k_select)
+                const int pep0 = b.pep_off[p], L = b.pep_off[p + 1] - pep0;
+                uint64_t slo = 0, shi = 0;
+                if (a.ascores)
+                    for (int i = 0; i < L; i++) {
+                        const int c = (int)b.pep[pep0 + i] - 'A';
+                        const bool is = ((c >= 0 && c < 26) && ((cfg.mod_letters >> c) & 1u)) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == L - 1);
+                        if (is) { if (i < 64) slo |= 1ull << i; else shi |= 1ull << (i - 64); }
+                    }
+                const uint64_t all = (S >= 64) ? ~0ull : ((1ull << S) - 1ull);
+                const uint64_t free_sites = all & ~best_bits;
+                uint64_t rem = best_bits;
+                for (int j = 0; j < k; j++) {
+                    const int site = __ffsll((long long)rem) - 1;
+                    rem &= rem - 1;
+                    // tied best competitors of this site (cpp/Ascore.cpp:212-254)
+                    float m = -INF;
+                    uint64_t tie = 0;
+                    for (uint64_t f = free_sites; f; f &= f - 1) {
+                        const int u = __ffsll((long long)f) - 1;
+                        const float w = a.iso.w[ib + pa_rank(cfg.binom, S, k, (best_bits & ~(1ull << site)) | (1ull << u))];
+                        if (w > m) { m = w; tie = 1ull << u; }
+                        else if (w == m) tie |= 1ull << u;
+                    }
+                    if (a.alt_sites) a.alt_sites[mo + j] = tie;
+                    a.tie[mo + j - a.mod_lo] = tie;
+                    a.mod_psm[mo + j - a.mod_lo] = (int32_t)p;
+                    if (a.ascores) {
+                        uint32_t key = PA_WORK_NONE;
+                        // every tied competitor has exactly the score m; within 1e-6 of the best score the
+                        // ambiguity is 0 without looking at any ion (cpp/Ascore.cpp:161-163)
+                        if ((double)fabsf(__fsub_rn(wb, m)) < 1e-6) a.ascores[mo + j] = 0.f;
+                        else {
+                            const int Z = b.max_charge[p];
+                            const int cls = cfg.has_nl ? 3 : (Z == 1 ? 0 : (Z == 2 ? 1 : (Z <= 4 ? 2 : 3)));
+                            atomicAdd(&s_cls[cls], 1);
+                            int work = 0;
+                            const int ps = pa_nth_set(slo, shi, site);
+                            for (uint64_t tt = tie; tt; tt &= tt - 1) {
+                                const int pu = pa_nth_set(slo, shi, __ffsll((long long)tt) - 1);
+                                work += (L - 1) + 3 * (pu > ps ? pu - ps : ps - pu);
+                            }
+                            work *= Z < 8 ? Z : 8;
+                            key = ((uint32_t)cls << 10) | (((uint32_t)(1023 - (work > 1023 ? 1023 : work)) >> PA_WORK_SHIFT) << PA_WORK_SHIFT);
+                        }
+                        a.work_key[mo + j - a.mod_lo] = (uint16_t)key;
+                        a.work_val[mo + j - a.mod_lo] = (int32_t)(mo + j - a.mod_lo);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cls[threadIdx.x]) atomicAdd(a.work_count + threadIdx.x, s_cls[threadIdx.x]);
+}
+
 // K3a: warp per PSM.  Best isoform in the reference's order + per modified site the set of tied
 // best competitors (= alternative sites).  The Ascore of every (PSM, site) entry is then computed
 // by k_ascore (thread per entry) or, for the rare shapes that kernel does not cover, k_ascore_generic.
@@ -1111,9 +1256,10 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
     if (lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)grab);
     int64_t run0 = (int64_t)__shfl_sync(PA_FULL, pend, 0);
     const bool ahead = a.grab > 0;                    // see k_count_score
-    while (run0 < a.n_psm) {
+    const int64_t n_visit = a.n_psm_dev ? (int64_t)*a.n_psm_dev : a.n_psm;
+    while (run0 < n_visit) {
       if (ahead && lane == 0) pend = atomicAdd(a.next_psm, (unsigned long long)grab);
-      const int64_t pi_end = run0 + grab < a.n_psm ? run0 + grab : a.n_psm;
+      const int64_t pi_end = run0 + grab < n_visit ? run0 + grab : n_visit;
       for (int64_t pi = run0; pi < pi_end; pi++) {
         const int64_t p = a.order ? a.order[pi] : pi;
         const int status = a.psm_status[p];

@@ -60,7 +60,7 @@ struct Slot {                // per-stream working set
     // plan
     DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
     // K2/K3
-    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, sched, best_idx, mod_psm, tie, generic_list, generic_count, work_key, work_key2, work_val, work_sorted;
+    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, sched, best_idx, mod_psm, tie, generic_list, generic_count, work_key, work_key2, work_val, work_sorted, rest_list;
     // staged outputs
     DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
     PlanTotals* h_totals = nullptr;      // pinned
@@ -70,7 +70,7 @@ struct Slot {                // per-stream working set
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rpk, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_totals) cudaFreeHost(h_totals);
@@ -866,13 +866,21 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.work_count = sl.generic_count.as<int>() + 1;
         sa.order = nullptr;                      // PSMs in input order: the Ascore entries are sorted by key below
         sa.next_psm = sl.sched.as<unsigned long long>() + 1;
+        // thread per PSM for the common shapes; what it declines (generic_count[5] PSMs in rest_list) goes to
+        // the warp-per-PSM kernel, whose visit count is therefore only known on the device
+        CK(sl.rest_list.ensure((size_t)std::max<int64_t>(np, 1) * 4));
+        sa.rest_list = sl.rest_list.as<int32_t>(); sa.rest_count = sl.generic_count.as<int>() + 5;
+        sa.n_psm_dev = nullptr; sa.grab = 1;
+        k_select_thread<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->cfg, cs.b, sa);
+        CK(cudaGetLastError());
         const int wpb = 8;
         const size_t sel_smem = wpb * PA_SORTCAP * sizeof(unsigned long long);
         int blocks = (int)std::min<int64_t>((np + wpb - 1) / wpb, (int64_t)s->sm_count * resident_blocks(k_select, wpb * 32, sel_smem));
-        sa.grab = grab_size(np, (int64_t)blocks * wpb, PA_SEL_GRAB);
+        sa.order = sl.rest_list.as<int32_t>(); sa.n_psm_dev = sl.generic_count.as<int>() + 5;
+        sa.grab = -1;                            // one PSM per visit, no reservation: the rest list is short
         k_select<<<blocks, wpb * 32, sel_smem, st>>>(s->cfg, cs.b, sa);
         CK(cudaGetLastError());
-        s->ctr.kernel_launches++; s->ctr.launches_select++;
+        s->ctr.kernel_launches += 2; s->ctr.launches_select += 2;
     }
     CK(cudaEventRecord(cs.e_sel1, st));
     if (np > 0 && nm > 0 && cs.o_asc != nullptr) {
