@@ -19,6 +19,9 @@
 #include "pa_probes.cuh"
 
 #define PA_VERSION 100
+#ifndef PA_K2_THREAD_DEFAULT
+#define PA_K2_THREAD_DEFAULT 0          // 1: k_count_thread is the default form of K2 for two ion types
+#endif
 #define PA_CHUNK_PSM 131072
 #define PA_CHUNK_PEAKS (96ll << 20)     // peaks per chunk (1.5 GB of float64 pairs)
 #define PA_TABLE_MIN 512
@@ -600,9 +603,6 @@ static cudaError_t copy_out(const DevBuf& buf, T* dst, bool on_dev, int64_t lo, 
 // 1 chunk 91.5 M PSM/s, 2 chunks 94.1 M, 4 chunks 84.0 M, 8 chunks 70.2 M -- the persistent kernels of two
 // chunks cannot share an SM (registers / shared memory), so more chunks only add launches and tails.  One
 // chunk keeps the per-kernel event times free of overlap, which the roofline arithmetic relies on.
-#ifndef PA_K2_THREAD_DEFAULT
-#define PA_K2_THREAD_DEFAULT 0          // 1: k_count_thread is the default form of K2 for two ion types
-#endif
 #ifndef PA_DEV_CHUNKS
 #define PA_DEV_CHUNKS 1
 #endif
