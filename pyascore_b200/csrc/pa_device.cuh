@@ -176,7 +176,6 @@ struct PsmInfo {
     int L, k, Z, S, R;
     int status;
     const float2* gp;             // global peaks {mz, rank bits} (used when they are not staged: cell == nullptr)
-    const uint8_t* gcell;         // the spectrum's m/z cell index in global memory (thread-per-walk kernel), or nullptr
     const float2* pk;             // staged peaks in shared memory (cell != nullptr)
     const uint8_t* cell;          // -> smem cell index, or nullptr (binary search over global peaks)
     float cell_base, cell_inv;    // cell(x) = clamp(floor((x - base) * inv), 0, PA_NCELL-1)
@@ -243,7 +242,6 @@ __device__ __forceinline__ void pa_setup_psm(const PaCfg& cfg, const PaBatchDev&
         const float2 head = b.chead[sp];
         info.R = R;
         info.gp = b.rpk + off;
-        info.gcell = nullptr;
         info.cell_base = head.x;
         info.cell_inv = head.y;
         staged = R <= PA_RCAP && head.y != 0.f;
@@ -346,30 +344,17 @@ __device__ __forceinline__ int pa_match_rank(const PsmInfo& info, float f, float
     const float2* gp = info.gp;
     const int R = info.R;
     int a = 0;
-    if (info.gcell != nullptr && info.cell_inv != 0.f) {
-        // cell index read from global memory: every peak before it is <= lo (see above)
-        a = __ldg(info.gcell + pa_cell(lo, info.cell_base, info.cell_inv));
-    } else {
-        int n = R;                      // first index with mz > lo
-        while (n > 0) {
-            int h = n >> 1;
-            if (!(gp[a + h].x > lo)) { a += h + 1; n -= h + 1; } else n = h;
-        }
+    int n = R;                          // first index with mz > lo
+    while (n > 0) {
+        int h = n >> 1;
+        if (!(gp[a + h].x > lo)) { a += h + 1; n -= h + 1; } else n = h;
     }
-    if (a < R) {
-        float2 e = __ldg(gp + a);
-        float2 e_next = __ldg(gp + (a + 1 < R ? a + 1 : R - 1));
-        for (;;) {
-            if (!(e.x < hi)) break;
-            if (e.x > lo && !(err_gt_half && !((double)f >= (double)e.x - .5))) {
-                const int r = __float_as_int(e.y);
-                best = r < best ? r : best;
-            }
-            if (++a >= R) break;
-            e = e_next;
-            if (!(e.x < hi)) break;
-            e_next = __ldg(gp + (a + 1 < R ? a + 1 : R - 1));
-        }
+    for (; a < R; a++) {
+        const float2 e = gp[a];
+        if (!(e.x < hi)) break;
+        if (err_gt_half && !((double)f >= (double)e.x - .5)) continue;
+        const int r = __float_as_int(e.y);
+        best = r < best ? r : best;
     }
     return best;
 }

@@ -1907,117 +1907,6 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
     if (a.ascores) a.ascores[a.mod_lo + t] = asc;
 }
 
-// ---------------------------------------------------------------------------------------------
-// K2, thread form: one THREAD per (isoform, ion type) walk, indexed across PSM boundaries.
-// The warp form above gives a PSM to a warp, which for the dozen isoforms of a typical PSM means
-// partly filled rounds, split walks with replayed sums and a table build per PSM.  Here every lane
-// carries one whole walk: residue masses come from the peptide bytes (asc_res), matches go to the
-// spectrum's packed peaks and cell index in global memory (neighbouring lanes belong to the same
-// PSM, so both stay in L1), fragment arithmetic and counting are the shared pa_emit_step.  Used for
-// exactly two ion types (the two walks of an isoform sit in neighbouring lanes).
-// ---------------------------------------------------------------------------------------------
-#ifndef PA_K2T_MINBLOCKS
-#define PA_K2T_MINBLOCKS 8
-#endif
-template <bool HAS_NL, bool EGH>
-__global__ void __launch_bounds__(128, PA_K2T_MINBLOCKS) k_count_thread(PaCfg cfg, PaBatchDev b, PaCountArgs a, int64_t n_iso,
-                                                                        int64_t n_psm) {
-    __shared__ ulonglong2 s_lut[16];
-    __shared__ float s_nl[HAS_NL ? 256 * 16 + 64 : 1];
-    if (threadIdx.x < 16) {
-        const int r = threadIdx.x;
-        s_lut[r] = make_ulonglong2(r < 5 ? 1ull << (12 * r) : 0ull, (r >= 5 && r < 10) ? 1ull << (12 * (r - 5)) : 0ull);
-    }
-    if (HAS_NL) {
-        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) s_nl[i] = cfg.nl_sums[i];
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) ((uint8_t*)(s_nl + 256 * 16))[i] = cfg.nl_nvar[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t g = t >> 1;                        // isoform, counted over the whole chunk
-    const int ty = (int)(t & 1);
-    const bool active = g < n_iso;
-    unsigned long long clo = 0, chi = 0;
-    uint32_t nf = 0;
-    int64_t p = 0;
-    uint32_t idx = 0;
-    if (active) {
-        // PSM of the isoform: binary search for the warp's first isoform (the same loads in every lane),
-        // then a short forward scan (a warp spans 16 isoforms)
-        const int64_t g0 = (t - lane) >> 1;
-        int64_t lo = 0, hi = n_psm;                  // largest p with iso_off[p] <= g0
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (a.iso_off[mid] <= g0) lo = mid; else hi = mid;
-        }
-        p = lo;
-        while (a.iso_off[p + 1] <= g) p++;
-        idx = (uint32_t)(g - a.iso_off[p]);
-        const int S = a.psm_S[p], k = b.n_mod[p];
-        AscPep q;
-        const int po = b.pep_off[p];
-        q.pep = b.pep + po; q.L = b.pep_off[p + 1] - po; q.Z = b.max_charge[p];
-        q.a0 = 0; q.a1 = 0; q.aux_pos = b.aux_pos; q.aux_mass = b.aux_mass; q.aux_lo = 0; q.aux_hi = 0;
-        if (b.aux_off != nullptr) {
-            q.a0 = b.aux_off[p]; q.a1 = b.aux_off[p + 1];
-            for (int x = q.a0; x < q.a1; x++) {
-                const uint32_t pos = q.aux_pos[x];
-                const int ix = pos > 0 ? (int)pos - 1 : 0;
-                if (ix < 64) q.aux_lo |= 1ull << ix; else if (ix < 128) q.aux_hi |= 1ull << (ix - 64);
-            }
-        }
-        const int sp = b.psm_spec[p];
-        const int64_t off = b.spec_off[sp] - b.spec_base;
-        PsmInfo info;
-        info.L = q.L; info.k = k; info.Z = q.Z; info.S = S; info.R = b.rcount[sp]; info.status = 0;
-        info.gp = b.rpk + off; info.pk = nullptr; info.cell = nullptr;
-        info.gcell = b.ctab + (size_t)sp * PA_NCELL;
-        { const float2 chead = b.chead[sp]; info.cell_base = chead.x; info.cell_inv = chead.y; }
-        // residue mask of the isoform: the set bits of its site subset, mapped to residue positions
-        const uint64_t bits = pa_unrank(cfg.binom, S, k, idx);
-        uint64_t mlo = 0, mhi = 0;
-        {
-            int n = 0;
-            for (int i = 0; i < q.L && n < 64; i++) {
-                const int c = (int)q.pep[i] - 'A';
-                const bool is = ((cfg.mod_letters >> c) & 1u) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == q.L - 1);
-                if (!is) continue;
-                if ((bits >> n) & 1ull) { if (i < 64) mlo |= 1ull << i; else mhi |= 1ull << (i - 64); }
-                n++;
-            }
-        }
-        const char type = cfg.types[ty];
-        const bool fwd = (type == 'b' || type == 'c');
-        double a1, a2;
-        pa_type_consts(type, a1, a2);
-        const double zm1 = c_zmass[1], zm2 = c_zmass[2];
-        const int L = q.L, steps = (L == 1) ? 1 : L - 1;
-        float run = 0.f;
-        int nls = 0;
-        for (int step = 0; step < steps; step++) {
-            const int i = fwd ? step : L - 1 - step;
-            const int st = (int)(((i < 64) ? (mlo >> i) : (mhi >> (i - 64))) & 1ull);
-            int nli;
-            run = __fadd_rn(asc_res(cfg, q, i, st, nli), run);      // r + 0.f == r: the first step needs no special case
-            if (HAS_NL) { if (nli) nls = pa_nl_bump(nls, nli); }
-            nf += pa_emit_step<HAS_NL, EGH>(cfg, info, s_nl, run, nls, a1, a2, zm1, zm2, s_lut, clo, chi);
-        }
-    }
-    unsigned long long lookups = nf;
-    // the two walks of an isoform sit in neighbouring lanes
-    clo += __shfl_xor_sync(PA_FULL, clo, 1);
-    chi += __shfl_xor_sync(PA_FULL, chi, 1);
-    nf += __shfl_xor_sync(PA_FULL, nf, 1);
-    if (active && ty == 0) {
-        pa_cumulate(clo, chi);
-        a.iso.lo[g] = clo; a.iso.hi[g] = chi; a.iso.nfrag[g] = nf;
-        a.iso.w[g] = pa_weighted(cfg, clo, chi, (int)nf);
-    }
-    for (int o = 16; o > 0; o >>= 1) lookups += __shfl_xor_sync(PA_FULL, lookups, o);
-    if (lane == 0 && lookups) atomicAdd(a.n_lookups, lookups);
-}
-
 // One launch per stream class (0: one charge, 1: two, 2: up to four, 3: neutral losses or more
 // charges), so that each instantiation gets its own register budget and occupancy.
 #ifndef PA_ASC_MINBLOCKS

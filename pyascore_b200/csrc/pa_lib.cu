@@ -19,9 +19,6 @@
 #include "pa_probes.cuh"
 
 #define PA_VERSION 100
-#ifndef PA_K2_THREAD_DEFAULT
-#define PA_K2_THREAD_DEFAULT 0          // 1: k_count_thread is the default form of K2 for two ion types
-#endif
 #define PA_CHUNK_PSM 131072
 #define PA_CHUNK_PEAKS (96ll << 20)     // peaks per chunk (1.5 GB of float64 pairs)
 #define PA_TABLE_MIN 512
@@ -123,7 +120,6 @@ struct pa_scorer {
     size_t ev_used = 0;
     int attr_set = 0;
     bool binner_only = false;
-    bool k2_thread = false;                // K2 as thread-per-walk (two ion types); PYASCORE_B200_K2=thread|warp overrides the default
 };
 
 // Blocks of `kernel` one SM keeps resident at this block size and dynamic shared memory: the
@@ -474,7 +470,6 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
     s = new pa_scorer();
     s->device = device;
     s->binner_only = binner_only;
-    { const char* e = getenv("PYASCORE_B200_K2"); s->k2_thread = PA_K2_THREAD_DEFAULT ? !(e && strcmp(e, "warp") == 0) : (e && strcmp(e, "thread") == 0); }
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     s->mod_group = mod_group; s->frag_types = fragment_types;
     s->bin_size = bin_size; s->mod_mass = mod_mass; s->err = mz_error; s->n_top = n_top;
@@ -819,16 +814,6 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
             ca.grab = grab_size(n_units, (int64_t)blocks * wpb, PA_K2_GRAB); \
             k_count_score<NL, PR, EG><<<blocks, wpb * 32, smem, st>>>(s->cfg, cs.b, ca); }
         const int variant = (s->cfg.has_nl ? 4 : 0) | (pair ? 2 : 0) | (s->cfg.err_gt_half ? 1 : 0);
-        if (pair && s->k2_thread && total_iso > 0) {
-            // thread per (isoform, ion type) walk over the whole chunk
-            const unsigned tb = (unsigned)((2 * total_iso + 127) / 128);
-            switch (variant & 5) {
-                case 0: k_count_thread<false, false><<<tb, 128, 0, st>>>(s->cfg, cs.b, ca, total_iso, np); break;
-                case 1: k_count_thread<false, true><<<tb, 128, 0, st>>>(s->cfg, cs.b, ca, total_iso, np); break;
-                case 4: k_count_thread<true, false><<<tb, 128, 0, st>>>(s->cfg, cs.b, ca, total_iso, np); break;
-                default: k_count_thread<true, true><<<tb, 128, 0, st>>>(s->cfg, cs.b, ca, total_iso, np); break;
-            }
-        } else
         switch (variant) {
             case 0: PA_K2_LAUNCH(false, false, false) break;
             case 1: PA_K2_LAUNCH(false, false, true) break;

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(32) k_sdi_probe(PaCfg cfg, PaBatchDev b, PaSdi
     PsmInfo info;
     pa_setup_psm(cfg, b, 0, &sm->psm, info, false);
     info.Z = a.max_charge;
-    info.R = 0; info.gp = nullptr; info.gcell = nullptr; info.pk = nullptr; info.cell = nullptr;
+    info.R = 0; info.gp = nullptr; info.pk = nullptr; info.cell = nullptr;
     info.cell_base = 0.f; info.cell_inv = 0.f;
     float* raw0 = sm->raw[0]; float* raw1 = sm->raw[1]; float* srt0 = sm->srt[0]; float* srt1 = sm->srt[1];
     long long per_type = (long long)(info.L > 1 ? info.L - 1 : 1) * cfg.nvar_cap * info.Z;

@@ -66,15 +66,8 @@ def check_against_ref(scorer, batch, ref, check_tables=True, exact_floats=True):
     return res
 
 
-# K2 exists in two forms (warp per PSM, thread per isoform walk; PYASCORE_B200_K2 picks one at pa_create):
-# both must reproduce the goldens and the oracle bit for bit
-K2_FORMS = ["warp", "thread"]
-
-
-@pytest.mark.parametrize("k2", K2_FORMS)
 @pytest.mark.parametrize("name", _golden.golden_names())
-def test_golden(name, k2, monkeypatch):
-    monkeypatch.setenv("PYASCORE_B200_K2", k2)
+def test_golden(name):
     meta, batch, ref = _golden.load(name)
     s = make_scorer(meta)
     check_against_ref(s, batch, ref)
@@ -98,11 +91,9 @@ def oracle_reference(meta, batch, idx):
     return out
 
 
-@pytest.mark.parametrize("k2", K2_FORMS)
 @pytest.mark.parametrize("workload,n", [("lowres_phospho", 6000), ("hires_phospho_nl", 3000), ("acetyl_k", 3000)])
-def test_live_oracle(workload, n, k2, monkeypatch):
+def test_live_oracle(workload, n):
     """larger seeded batch (different seed from the goldens): every PSM against the C oracle"""
-    monkeypatch.setenv("PYASCORE_B200_K2", k2)
     from pyascore_b200 import Scorer, format_results
     w = synth.WORKLOADS[workload]
     meta = dict(scorer=w["scorer"], neutral_losses=w["neutral_losses"])
