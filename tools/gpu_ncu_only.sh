@@ -1,14 +1,10 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, bench at the BASELINE size, ncu launch list and full captures.
-# usage: tools/gpu_check.sh <tag>     (outputs under gpurun_out/<tag>_*)
+# ncu launch list + full-set capture of one timed step (no tests, no bench).  usage: tools/gpu_ncu_only.sh <tag>
 TAG=${1:-run}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
-tail -3 gpurun_out/${TAG}_pytest.log
-python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench.json
 PROF="python bench.py --psms 262144 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
 timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 200 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $PROF > gpurun_out/${TAG}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_bin_topn|k_count_score|k_select|k_ascore$' -s 24 -c 8 \
     -f -o gpurun_out/${TAG}_prof $PROF > gpurun_out/${TAG}_ncu_full.log 2>&1
-ls -la gpurun_out | tail -12
+ls -la gpurun_out | grep ${TAG}

@@ -17,7 +17,7 @@ for r in body:
     tot = 0.
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[ix[m]].replace(",", "")) * scale[units[ix[m]]]
-    key = {"k_bin_topn": "bin_topn", "k_select": "select"}.get(name, "count_score" if name.startswith("k_count_score") else
+    key = {"k_bin_topn": "bin_topn", "k_select": "select", "k_select_thread": "select"}.get(name, "count_score" if name.startswith("k_count_score") else
                                                              "ascore" if name.startswith("k_ascore") else name)
     e = out.setdefault(key, {"dram_bytes_per_psm": 0., "warp_inst_per_psm": 0., "kernels": []})
     e["dram_bytes_per_psm"] += tot / n
