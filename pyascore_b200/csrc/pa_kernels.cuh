@@ -1,9 +1,12 @@
-// Kernels of libpyascore_b200 (sm_100a).  One warp owns one unit of domain work:
-//   K0 k_tail_table   one block per trial count n: float32-faithful binomial score table
-//   K1 k_bin_topn     one warp per spectrum: top-n_top peaks per bin_size-Th bin (BinnedSpectra)
-//   P1 k_plan         one thread per PSM: validation, #sites, #isoforms, work units
-//   K2 k_count_score  one warp per unit of <=1024 positional isoforms: fragments, matches, PepScore
-//   K3 k_select       one warp per PSM: reference-order best isoform, Ascores, alternative sites
+// Kernels of libpyascore_b200 (sm_100a).  The unit of domain work decides who owns it:
+//   K0  k_tail_table     one block per trial count n: float32-faithful binomial score table
+//   K1  k_bin_topn       one warp per spectrum: top-n_top peaks per bin_size-Th bin (BinnedSpectra)
+//   P1  k_plan           one thread per PSM: validation, #sites, #isoforms, work units
+//   K2  k_count_score    one warp per unit of <=1024 positional isoforms: fragments, matches, PepScore
+//   K3a k_select_thread  one thread per PSM: reference-order best isoform, tied competitors per site,
+//                        sort keys of the Ascore entries; k_select (one warp per PSM) for the PSMs it declines
+//   K3b k_ascore         one thread per (PSM, modified site): site-determining-ion merges -> Ascore
+//   K3c k_ascore_generic one warp per entry: list-materialising form for the shapes K3b declines
 // Nothing here is a dense contraction: no tensor cores.  The work is integer / float32 / a little
 // FP64 per fragment, bound by instruction issue and shared-memory latency.
 #pragma once
