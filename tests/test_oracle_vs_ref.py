@@ -92,3 +92,20 @@ def test_get_peptide_equals_reference():
         for sig in ([], [0, 1, 0, 1], [1], [0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]):
             s = np.array(sig, np.int32)
             assert R.get_peptide(s) == O.get_peptide(s), (pep, sig)
+
+
+@pytest.mark.parametrize("n_top,bin_size", [(10, 100.), (40, 100.), (3, 25.), (254, 1000.), (12, 2.5)])
+def test_binning_equals_reference_on_awkward_intensities(n_top, bin_size):
+    """BinnedSpectra on the inputs the GPU binning tests lean on the oracle for: intensities that are distinct
+    as doubles but collide as floats, values far outside the float range, negative intensities, many bins"""
+    rng = np.random.default_rng(31)
+    O = cscorer.OraclePyAscore(bin_size, n_top, "STY", 79.966331)
+    R = cscorer.RefPyAscore(bin_size, n_top, "STY", 79.966331)
+    n = 900
+    mz = np.sort(rng.uniform(300., 1800., n))
+    cases = [5000. + rng.permutation(n) * 1e-7,
+             np.where(rng.random(n) < 0.3, 321.5 + rng.permutation(n) * 1e-9, rng.lognormal(5., 1., n)),
+             rng.standard_normal(n) * 10. ** rng.integers(-60, 60, n)]
+    for inten in cases:
+        a, b = O.binned(mz, inten), R.binned(mz, inten)
+        assert all(np.array_equal(a[k], b[k]) for k in a)
