@@ -30,9 +30,9 @@ typedef struct pa_scorer pa_scorer;
 typedef enum {
     PA_OK = 0,
     PA_ERR_CUDA = -1,        /* CUDA runtime / driver error (text in pa_last_error) */
-    PA_ERR_ARG = -2,         /* invalid argument (NULL pointer, bad fragment type, n_top != 10 ...) */
+    PA_ERR_ARG = -2,         /* invalid argument (NULL pointer, bad fragment type, inconsistent CSR arrays ...) */
     PA_ERR_UNSUPPORTED = -3, /* outside the supported envelope (see limits below) */
-    PA_ERR_STATE = -4        /* call needs a kept batch (PA_KEEP_ISOFORMS) and there is none */
+    PA_ERR_STATE = -4        /* call needs a kept batch (PA_KEEP_ISOFORMS) and there is none, or an asynchronous call is in flight */
 } pa_status;
 
 /* per-PSM status written to pa_results.psm_status (0 = scored) */
@@ -110,6 +110,37 @@ typedef struct {
 /* Replaces PyAscore.score for n_psm PSMs at once (Ascore.pyx:103-152 -> cpp/Spectra.cpp:43-68,
  * cpp/ModifiedPeptide.cpp:105-150, cpp/Ascore.cpp:256-271).  Synchronous: results are complete on return. */
 int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results* out, uint32_t flags);
+
+/* The same for PSMs [psm_lo, psm_hi) of the batch only.  Results land at their ABSOLUTE positions in `out`
+ * (best_sig[p], ascores[mod_off[p] + j], ...), so several scorers -- one per GPU -- can each take a range of one
+ * batch and fill one set of result arrays without a gather step: the sharded form of the loop in
+ * pyascore/__main__.py:129-164 (pyascore_b200/shard.py cuts the ranges on spectrum boundaries). */
+int pa_score_range(pa_scorer* s, const pa_batch* in, const pa_results* out, int64_t psm_lo, int64_t psm_hi,
+                   uint32_t flags);
+
+/* Asynchronous form of pa_score_range: returns once the work is handed to the scorer's own orchestration thread
+ * (the path takes one host decision per chunk -- the plan totals size the isoform scratch -- so it cannot be a
+ * pure stream enqueue).  `stream` (a cudaStream_t of the scorer's device, or NULL) is honoured as a dependency:
+ * everything queued on it before this call completes before the inputs are read.  psm_hi < 0 means n_psm.
+ * The arrays behind `in` / `out` must stay valid until pa_wait returns; the two structs themselves are copied.
+ * At most one call may be in flight per scorer (other entry points return PA_ERR_STATE meanwhile). */
+int pa_score_batch_async(pa_scorer* s, const pa_batch* in, const pa_results* out, int64_t psm_lo, int64_t psm_hi,
+                         uint32_t flags, void* stream);
+
+/* Blocks until the call started by pa_score_batch_async is complete and returns its status
+ * (PA_OK at once when nothing is in flight).  Results and pa_counters are valid afterwards. */
+int pa_wait(pa_scorer* s);
+
+/* Cut points for sharding a HOST batch over `world` scorers (one per GPU): cuts[0] = 0 <= cuts[1] <= ... <=
+ * cuts[world] = n_psm, rank r takes PSMs [cuts[r], cuts[r+1]).  psm_spec must be non-decreasing (scan-sorted PSMs,
+ * as pyascore/__main__.py:38-44 sorts them); cuts never split the hits of one spectrum.  Ranges are balanced by
+ * estimated cost: isoforms x fragments + peak_weight x peaks of the spectrum / its hits (peak_weight ~ 55 for host
+ * inputs, where the host -> device copy of the peaks dominates; ~ 4 for kernel time alone).  Host arithmetic only. */
+int pa_shard_ranges(const pa_scorer* s, const pa_batch* in, int32_t world, double peak_weight, int64_t* cuts);
+/* The same without a scorer handle (no GPU needed): mod_group as given to pa_create, the number of ion types and
+ * the largest neutral-loss variant count per residue (1 without neutral losses). */
+int pa_shard_ranges_for(const char* mod_group, int32_t n_types, int32_t nl_variants, const pa_batch* in,
+                        int32_t world, double peak_weight, int64_t* cuts);
 
 /* Replaces the pep_scores property (Ascore.pyx:240-252 -> cpp/Ascore.cpp:281-303) for PSM
  * `psm` of the last batch scored with PA_KEEP_ISOFORMS.  Rows come in the reference's order

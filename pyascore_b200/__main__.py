@@ -11,7 +11,7 @@ from datetime import datetime
 
 import numpy as np
 
-from .batch import Scorer
+from .batch import MultiScorer, Scorer
 from .config import args_from_file, build_parser, validate_args
 from .parsing import (COMMON_MODS, IdentificationParser, MassCorrector, SpectraParser, iter_batches, result_rows,
                       score_stream, write_tsv)
@@ -42,7 +42,11 @@ def parse_identifications(args):
 
 def build_scorer(args):
     """reference: __main__.py:68-80 (bin_size 100, n_top 10 are fixed there too)"""
-    scorer = Scorer(100., 10, args.residues, args.mod_mass, args.mz_error, args.fragment_types, device=args.device)
+    devices = [int(d) for d in getattr(args, "devices", "").split(",") if d.strip() != ""]
+    if devices:
+        scorer = MultiScorer(100., 10, args.residues, args.mod_mass, args.mz_error, args.fragment_types, devices=devices)
+    else:
+        scorer = Scorer(100., 10, args.residues, args.mod_mass, args.mz_error, args.fragment_types, device=args.device)
     if args.neutral_loss_groups and args.neutral_loss_masses:
         for g, m in zip(args.neutral_loss_groups.split(","), args.neutral_loss_masses.split(",")):
             scorer.add_neutral_loss(g, float(m))

@@ -46,7 +46,7 @@ EXPORTS = ["pa_create", "pa_add_neutral_loss", "pa_destroy", "pa_last_error", "p
            "pa_fetch_pep_scores", "pa_calculate_ambiguity", "pa_format_sequence", "pa_site_positions",
            "pa_bin_spectra", "pa_tail_table", "pa_counters", "pa_alloc_pinned", "pa_free_pinned", "pa_version",
            "pa_create_binner", "pa_bin_spectra_ex", "pa_fragment_table", "pa_site_determining_ions", "pa_log_math",
-           "pa_power_set_sums"]
+           "pa_power_set_sums", "pa_score_range", "pa_score_batch_async", "pa_wait", "pa_shard_ranges", "pa_shard_ranges_for"]
 
 _lib = None
 
@@ -71,6 +71,16 @@ def load():
     L.pa_last_error.argtypes = [vp]
     L.pa_score_batch.restype = C.c_int
     L.pa_score_batch.argtypes = [vp, C.POINTER(PaBatch), C.POINTER(PaResults), C.c_uint32]
+    L.pa_score_range.restype = C.c_int
+    L.pa_score_range.argtypes = [vp, C.POINTER(PaBatch), C.POINTER(PaResults), C.c_int64, C.c_int64, C.c_uint32]
+    L.pa_score_batch_async.restype = C.c_int
+    L.pa_score_batch_async.argtypes = [vp, C.POINTER(PaBatch), C.POINTER(PaResults), C.c_int64, C.c_int64, C.c_uint32, vp]
+    L.pa_wait.restype = C.c_int
+    L.pa_wait.argtypes = [vp]
+    L.pa_shard_ranges.restype = C.c_int
+    L.pa_shard_ranges.argtypes = [vp, C.POINTER(PaBatch), C.c_int32, C.c_double, vp]
+    L.pa_shard_ranges_for.restype = C.c_int
+    L.pa_shard_ranges_for.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(PaBatch), C.c_int32, C.c_double, vp]
     L.pa_fetch_pep_scores.restype = C.c_int64
     L.pa_fetch_pep_scores.argtypes = [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp]
     L.pa_calculate_ambiguity.restype = C.c_int

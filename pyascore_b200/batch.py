@@ -21,6 +21,9 @@ _OUT_DTYPES = dict(best_sig=np.uint64, best_score=np.float32, n_iso=np.int64, n_
                    ascores=np.float32, alt_sites=np.uint64, psm_status=np.int32)
 
 
+_WANT_ALL = ("best_sig", "best_score", "n_iso", "n_sites", "ascores", "alt_sites", "psm_status")
+
+
 class _Pinned:
     """numpy view over cudaMallocHost memory; freed when the last view dies."""
 
@@ -61,11 +64,11 @@ def add_mod_off(batch):
         n_mod = batch["n_mod"]
         if isinstance(n_mod, np.ndarray):
             mo = np.zeros(n_mod.size + 1, np.int64)
-            np.cumsum(n_mod, out=mo[1:])
+            np.cumsum(np.maximum(n_mod, 0), out=mo[1:])      # (a negative n_mod is reported per PSM, not laid out)
         else:  # torch tensor
             import torch
             mo = torch.zeros(n_mod.numel() + 1, dtype=torch.int64, device=n_mod.device)
-            mo[1:] = torch.cumsum(n_mod.to(torch.int64), 0)
+            mo[1:] = torch.cumsum(n_mod.to(torch.int64).clamp_(min=0), 0)
         batch["mod_off"] = mo
     return batch
 
@@ -130,9 +133,8 @@ class Scorer:
         if rc != 0:
             self._raise(rc)
 
-    def score_batch(self, batch, out=None, keep_isoforms=False, want=("best_sig", "best_score", "n_iso", "n_sites",
-                                                                      "ascores", "alt_sites", "psm_status")):
-        """Score every PSM of `batch`; returns dict of result arrays (same side as the inputs)."""
+    def _prepare(self, batch, out, want):
+        """checked ctypes views of a batch + result arrays (allocated on the side the inputs live on)"""
         add_mod_off(batch)
         for k in _IN_KEYS:
             if k in batch and batch[k] is not None:
@@ -162,10 +164,54 @@ class Scorer:
         pr = _lib.PaResults()
         for k in _OUT_DTYPES:
             setattr(pr, k, _ptr(out.get(k)))
-        rc = self.L.pa_score_batch(self.h, C.byref(pb), C.byref(pr), _lib.PA_KEEP_ISOFORMS if keep_isoforms else 0)
+        return pb, pr, out
+
+    def score_batch(self, batch, out=None, keep_isoforms=False, want=_WANT_ALL, psm_range=None):
+        """Score every PSM of `batch` (or PSMs [lo, hi) with psm_range=(lo, hi): results land at their absolute
+        positions); returns dict of result arrays (same side as the inputs)."""
+        pb, pr, out = self._prepare(batch, out, want)
+        flags = _lib.PA_KEEP_ISOFORMS if keep_isoforms else 0
+        if psm_range is None:
+            rc = self.L.pa_score_batch(self.h, C.byref(pb), C.byref(pr), flags)
+        else:
+            rc = self.L.pa_score_range(self.h, C.byref(pb), C.byref(pr), int(psm_range[0]), int(psm_range[1]), flags)
         if rc != 0:
             self._raise(rc)
         return out
+
+    def score_batch_async(self, batch, out=None, want=_WANT_ALL, psm_range=None, stream=None):
+        """Start scoring and return at once (pa_score_batch_async); `wait()` completes the call.  `stream`: a CUDA
+        stream handle (int / torch.cuda.Stream) whose queued work must finish before the inputs are read."""
+        pb, pr, out = self._prepare(batch, out, want)
+        lo, hi = (0, -1) if psm_range is None else (int(psm_range[0]), int(psm_range[1]))
+        if stream is not None and not isinstance(stream, int):
+            stream = stream.cuda_stream
+        self._inflight = (batch, out)            # the arrays must outlive the call
+        rc = self.L.pa_score_batch_async(self.h, C.byref(pb), C.byref(pr), lo, hi, 0, stream)
+        if rc != 0:
+            self._inflight = None
+            self._raise(rc)
+        return out
+
+    def wait(self):
+        rc = self.L.pa_wait(self.h)
+        self._inflight = None
+        if rc != 0:
+            self._raise(rc)
+
+    def shard_ranges(self, batch, world, peak_weight=55.):
+        """-> [(p0, p1)] * world: contiguous PSM ranges of a host batch cut on spectrum boundaries and balanced by
+        estimated cost (pa_shard_ranges)"""
+        add_mod_off(batch)
+        pb = _lib.PaBatch()
+        pb.n_spec, pb.n_psm = int(batch["spec_off"].shape[0]) - 1, int(batch["n_mod"].shape[0])
+        for k in _IN_KEYS:
+            setattr(pb, k, _ptr(batch.get(k)))
+        cuts = np.zeros(world + 1, np.int64)
+        rc = self.L.pa_shard_ranges(self.h, C.byref(pb), int(world), float(peak_weight), cuts.ctypes.data)
+        if rc != 0:
+            raise ValueError("pyascore_b200: cannot shard this batch (host arrays with non-decreasing psm_spec needed)")
+        return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
 
     def counters(self):
         c = _lib.PaCounters()
@@ -241,6 +287,66 @@ class Scorer:
         pos = np.zeros(max(len(pb), 1), np.int32)
         n = self.L.pa_site_positions(self.h, arr.ctypes.data, len(pb), pos.ctypes.data, pos.size)
         return pos[:n]
+
+
+class MultiScorer:
+    """One scorer per GPU of the box behind the interface of `Scorer`: a host batch is cut into contiguous PSM
+    ranges on spectrum boundaries (balanced by estimated cost), every GPU scores its range concurrently and writes
+    its slice of ONE set of result arrays -- no collective, no gather (the sharded form of
+    the loop in pyascore/__main__.py:129-164)."""
+
+    def __init__(self, bin_size, n_top, mod_group, mod_mass, mz_error=.5, fragment_types="by", devices=(0,)):
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise ValueError("MultiScorer needs at least one device")
+        self.scorers = [Scorer(bin_size, n_top, mod_group, mod_mass, mz_error, fragment_types, device=d)
+                        for d in self.devices]
+        self.mod_group = mod_group
+        self.last_ranges = None
+
+    def close(self):
+        for sc in self.scorers:
+            sc.close()
+
+    def add_neutral_loss(self, group, mass):
+        for sc in self.scorers:
+            sc.add_neutral_loss(group, mass)
+
+    def score_batch(self, batch, out=None, want=_WANT_ALL, peak_weight=55.):
+        if not isinstance(batch["mz"], np.ndarray):
+            raise ValueError("MultiScorer shards host batches; device-resident batches belong to one GPU")
+        n = len(self.scorers)
+        if n == 1:
+            self.last_ranges = [(0, int(batch["n_mod"].shape[0]))]
+            return self.scorers[0].score_batch(batch, out=out, want=want)
+        self.last_ranges = ranges = self.scorers[0].shard_ranges(batch, n, peak_weight)
+        started = []
+        err = None
+        for sc, r in zip(self.scorers, ranges):
+            try:
+                out = sc.score_batch_async(batch, out=out, want=want, psm_range=r)     # rank 0 allocates `out`
+                started.append(sc)
+            except Exception as e:          # noqa: BLE001 -- the ranks already started must still be waited for
+                err = e
+                break
+        for sc in started:
+            try:
+                sc.wait()
+            except Exception as e:          # noqa: BLE001
+                err = err or e
+        if err is not None:
+            raise err
+        return out
+
+    def counters(self):
+        return [sc.counters() for sc in self.scorers]
+
+    # string / site helpers are host arithmetic: any scorer serves
+    def format_sequence(self, *a):
+        return self.scorers[0].format_sequence(*a)
+
+    def site_positions(self, pep):
+        return self.scorers[0].site_positions(pep)
 
 
 def format_results(scorer, batch, res, i):

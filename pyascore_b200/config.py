@@ -49,6 +49,8 @@ def build_parser():
     for flag, typ, default, text in _OPTIONS:
         p.add_argument(flag, type=typ, default=default, help=text)
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal.")
+    p.add_argument("--devices", type=str, default="", help="Comma separated CUDA device ordinals: every batch is "
+                   "sharded over these GPUs (overrides --device).")
     p.add_argument("--chunk_psms", type=int, default=65536, help="PSMs packed per GPU batch.")
     p.add_argument("spec_file", type=str, help="MS spectra file.")
     p.add_argument("ident_file", type=str, help="Results of the database search.")

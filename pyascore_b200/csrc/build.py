@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "libpyascore_b200.so")
 SRCS = ["pa_lib.cu"]
-DEPS = ["pa_lib.cu", "pa_kernels.cuh", "pa_device.cuh", "../../include/pyascore_b200.h"]
+DEPS = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh"))) + ["../../include/pyascore_b200.h"]
 
 
 def needs_build():
@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + [os.path.join(HERE, s) for s in SRCS]
+           "-fmad=false", "-Xcompiler", "-fPIC,-pthread", "-shared", "-o", OUT] + [os.path.join(HERE, s) for s in SRCS]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -480,8 +480,26 @@ __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n
         }
         int64_t I = 0;
         if (status == PA_PSM_OK) {
-            long long per_type = (long long)(L > 1 ? L - 1 : 1) * cfg.nvar_cap * Z;
-            long long nf = per_type * cfg.n_types;
+            // Upper bound of the fragments one isoform emits (all ion types, charges, neutral-loss variants).
+            // Without neutral losses it is exact.  With them, every residue is taken to push every loss it could
+            // carry in either state: the variant count only grows with the stack, so walking this superset bounds
+            // every real isoform (tighter than "worst state at every step", which rejected long high-charge peptides).
+            const int steps = L > 1 ? L - 1 : 1;
+            long long nf = (long long)steps * Z * cfg.n_types;
+            if (cfg.has_nl) {
+                long long tot[2] = {0, 0};
+                for (int dir = 0; dir < 2; dir++) {
+                    int st = 0;
+                    for (int step = 0; step < steps; step++) {
+                        const int c = (int)b.pep[off + (dir ? L - 1 - step : step)] - 'A';
+                        if (cfg.nl_upper[c]) st = pa_nl_bump(st, cfg.nl_upper[c]);
+                        if (cfg.nl_lower[c]) st = pa_nl_bump(st, cfg.nl_lower[c]);
+                        tot[dir] += cfg.nl_nvar[st];
+                    }
+                }
+                nf = 0;
+                for (int t = 0; t < cfg.n_types; t++) nf += tot[(cfg.types[t] == 'b' || cfg.types[t] == 'c') ? 0 : 1] * Z;
+            }
             if (nf > PA_MAX_FRAGMENTS) status = PA_PSM_TOO_MANY_FRAGMENTS;
             else {
                 uint32_t c = (k <= S) ? cfg.binom[S * 64 + k] : 0u;
@@ -489,7 +507,7 @@ __global__ void __launch_bounds__(256) k_plan(PaCfg cfg, PaBatchDev b, int64_t n
                 else {
                     I = c;
                     atomicMax(&s_max[0], (int)nf);
-                    atomicMax(&s_max[1], (int)per_type);
+                    atomicMax(&s_max[1], steps * cfg.nvar_cap * Z);      // the list kernels size their arenas by this looser bound
                     atomicMax(&s_max[2], L);
                     if (I > 1) atomicOr(&s_combo[S], 1ull << k);
                 }

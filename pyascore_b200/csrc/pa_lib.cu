@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -41,6 +42,13 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return (T*)p; }
+};
+
+struct TmpBuf : DevBuf {     // function-local scratch: freed on every return path
+    TmpBuf() = default;
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+    ~TmpBuf() { release(); }
 };
 
 struct PlanTotals {          // device -> host after planning a chunk
@@ -120,6 +128,12 @@ struct pa_scorer {
     size_t ev_used = 0;
     int attr_set = 0;
     bool binner_only = false;
+    // pa_score_batch_async: one orchestration thread per call in flight (at most one per scorer)
+    std::thread worker;
+    bool busy = false;
+    int async_rc = PA_OK;
+    pa_batch async_in;
+    pa_results async_out;
 };
 
 // Blocks of `kernel` one SM keeps resident at this block size and dynamic shared memory: the
@@ -337,7 +351,7 @@ static int ensure_table(pa_scorer* s, int n_max) {
     if (want < n_max) return fail(s, PA_ERR_UNSUPPORTED, "score table beyond %d trials", PA_MAX_FRAGMENTS);
     CK(cudaDeviceSynchronize());
     size_t entries = ((size_t)want + 1) * ((size_t)want + 2) / 2;
-    DevBuf nt;
+    TmpBuf nt;
     CK(nt.ensure(entries * PA_N_TOP * sizeof(float)));
     std::vector<double> logd(want + 2);
     logd[0] = 0.;
@@ -361,7 +375,8 @@ static int ensure_table(pa_scorer* s, int n_max) {
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     s->d_T.release();
-    s->d_T = nt;
+    s->d_T.p = nt.p; s->d_T.cap = nt.cap;
+    nt.p = nullptr; nt.cap = 0;              // ownership moved to the scorer
     s->table_n = want;
     s->cfg.T = s->d_T.as<float>();
     s->cfg.table_n = want;
@@ -425,8 +440,8 @@ static int upload_perms(pa_scorer* s) {
 
 static cudaEvent_t next_event(pa_scorer* s) {
     if (s->ev_used == s->ev_pool.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }   // cudaEventRecord(nullptr) then reports the failure
         s->ev_pool.push_back(e);
     }
     return s->ev_pool[s->ev_used++];
@@ -549,6 +564,7 @@ extern "C" int pa_add_neutral_loss(pa_scorer* s, const char* group, float mass) 
 
 extern "C" void pa_destroy(pa_scorer* s) {
     if (!s) return;
+    if (s->busy && s->worker.joinable()) s->worker.join();
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) s->slot[i].release();
@@ -608,6 +624,7 @@ struct DevBounds {
     int bad;                            // psm_spec decreasing or out of range somewhere
     int max_peaks;                      // largest spectrum of the batch
     int pad;
+    int64_t n_aux;                      // fixed-mod entries of the range
     int64_t p[PA_DEV_CHUNKS_MAX + 1];       // first PSM of chunk c (p[n] = n_psm)
     int64_t s0[PA_DEV_CHUNKS_MAX + 1];      // first spectrum chunk c references
     int64_t s1[PA_DEV_CHUNKS_MAX + 1];      // one past the last spectrum chunk c-1 references
@@ -616,13 +633,17 @@ struct DevBounds {
 };
 
 __global__ void k_dev_bounds(const int64_t* spec_off, const int32_t* psm_spec, const int32_t* pep_off,
-                             const int64_t* mod_off, int64_t n_psm, int64_t n_spec, int C, int64_t per, DevBounds* o) {
+                             const int32_t* aux_off, const int64_t* mod_off, int64_t p_lo, int64_t p_hi, int64_t n_spec,
+                             int C, int64_t per, DevBounds* o) {
     const int c = threadIdx.x;
-    if (c == 0) o->n = C;
+    if (c == 0) {
+        o->n = C;
+        o->n_aux = aux_off ? (int64_t)aux_off[p_hi] - (int64_t)aux_off[p_lo] : 0;
+    }
     if (c > C) return;
-    const int64_t p = (int64_t)c * per < n_psm ? (int64_t)c * per : n_psm;
-    int64_t s0 = p < n_psm ? (int64_t)psm_spec[p] : n_spec;
-    int64_t s1 = p > 0 ? (int64_t)psm_spec[p - 1] + 1 : 0;
+    const int64_t p = p_lo + (int64_t)c * per < p_hi ? p_lo + (int64_t)c * per : p_hi;
+    int64_t s0 = p < p_hi ? (int64_t)psm_spec[p] : (p_hi > p_lo ? (int64_t)psm_spec[p_hi - 1] + 1 : 0);
+    int64_t s1 = p > p_lo ? (int64_t)psm_spec[p - 1] + 1 : 0;
     s0 = s0 < 0 ? 0 : (s0 > n_spec ? n_spec : s0);
     s1 = s1 < 0 ? 0 : (s1 > n_spec ? n_spec : s1);
     o->p[c] = p; o->s0[c] = s0; o->s1[c] = s1;
@@ -630,13 +651,24 @@ __global__ void k_dev_bounds(const int64_t* spec_off, const int32_t* psm_spec, c
     o->pep[c] = pep_off[p]; o->mod[c] = mod_off[p];
 }
 
-__global__ void k_check_psm_spec(const int32_t* psm_spec, int64_t n_psm, int64_t n_spec, int* bad) {
-    bool b = false;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_psm; p += (int64_t)gridDim.x * blockDim.x) {
+// Consistency of a device-resident batch (the host path checks the same things per chunk): `bad` bit 0 =
+// psm_spec decreasing or out of range (the batch is then scored as one chunk over every spectrum),
+// bit 1 = an offset array is not a non-decreasing CSR index or mod_off does not follow n_mod (PA_ERR_ARG).
+__global__ void k_check_batch(const int32_t* psm_spec, const int32_t* pep_off, const int32_t* aux_off,
+                              const int32_t* n_mod, const int64_t* mod_off, const int64_t* spec_off, int64_t p_lo,
+                              int64_t p_hi, int64_t n_spec, int* bad) {
+    int b = 0;
+    for (int64_t p = p_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p_hi; p += (int64_t)gridDim.x * blockDim.x) {
         const int32_t v = psm_spec[p];
-        b |= v < 0 || v >= n_spec || (p > 0 && v < psm_spec[p - 1]);
+        if (v < 0 || v >= n_spec || (p > p_lo && v < psm_spec[p - 1])) b |= 1;
+        if (pep_off[p + 1] < pep_off[p] || pep_off[p] < 0) b |= 2;
+        if (aux_off && (aux_off[p + 1] < aux_off[p] || aux_off[p] < 0)) b |= 2;
+        if (mod_off[p + 1] - mod_off[p] != (int64_t)(n_mod[p] > 0 ? n_mod[p] : 0) || mod_off[p] < 0) b |= 2;
     }
-    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicExch(bad, 1);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_spec; q += (int64_t)gridDim.x * blockDim.x)
+        if (spec_off[q + 1] < spec_off[q] || spec_off[q] < 0) b |= 2;
+    for (int o = 16; o > 0; o >>= 1) b |= __shfl_xor_sync(0xffffffffu, b, o);
+    if (b && (threadIdx.x & 31) == 0) atomicOr(bad, b);
 }
 
 struct ChunkRange { int64_t p0, p1, s0, s1; };
@@ -937,30 +969,44 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     return PA_OK;
 }
 
-extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results* out, uint32_t flags) {
+// Host-side consistency check of PSMs [p0, p1) of a host batch and the spectra [s0, s1) they reference
+// (the device-resident path runs k_check_batch instead).  Called per chunk, so that all but the first
+// chunk's check overlaps the GPU work of the chunk before.
+static const char* check_host_range(const pa_batch* in, int64_t p0, int64_t p1, int64_t s0, int64_t s1) {
+    for (int64_t q = s0; q < s1; q++)
+        if (in->spec_off[q + 1] < in->spec_off[q] || in->spec_off[q] < 0) return "spec_off is not a non-decreasing CSR index";
+    for (int64_t p = p0; p < p1; p++) {
+        if (in->pep_off[p + 1] < in->pep_off[p] || in->pep_off[p] < 0) return "pep_off is not a non-decreasing CSR index";
+        if (in->aux_off && (in->aux_off[p + 1] < in->aux_off[p] || in->aux_off[p] < 0)) return "aux_off is not a non-decreasing CSR index";
+        if (in->mod_off[p + 1] - in->mod_off[p] != (int64_t)std::max(in->n_mod[p], 0) || in->mod_off[p] < 0)
+            return "mod_off is not the exclusive prefix sum of n_mod";
+    }
+    if (in->aux_off && in->aux_off[p1] > in->aux_off[p0] && (!in->aux_pos || !in->aux_mass)) return "aux_off is not empty but aux_pos / aux_mass is NULL";
+    return nullptr;
+}
+
+static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, int64_t p_lo, int64_t p_hi, uint32_t flags) {
     if (!s) return PA_ERR_ARG;
     if (!in || !out) return fail(s, PA_ERR_ARG, "NULL batch or results");
     if (s->binner_only) return fail(s, PA_ERR_STATE, "this handle was made by pa_create_binner: it only bins spectra");
     if (in->n_psm < 0 || in->n_spec < 0) return fail(s, PA_ERR_ARG, "negative sizes");
+    if (p_lo < 0 || p_hi > in->n_psm || p_lo > p_hi) return fail(s, PA_ERR_ARG, "PSM range [%lld, %lld) outside the batch of %lld", (long long)p_lo, (long long)p_hi, (long long)in->n_psm);
     if (in->n_psm > 0 && (!in->spec_off || !in->mz || !in->inten || !in->psm_spec || !in->pep_off || !in->pep ||
                           !in->n_mod || !in->max_charge || !in->mod_off))
         return fail(s, PA_ERR_ARG, "NULL input array");
-    if (in->aux_off && (!in->aux_pos || !in->aux_mass)) {
-        // an all-empty aux CSR may come with NULL payload pointers
-    }
     CK(cudaSetDevice(s->device));
-    int rc = refresh_config(s);
-    if (rc != PA_OK) return rc;
+    int rc = PA_OK;         // (the device-side config is current: pa_create / pa_add_neutral_loss refresh it)
     memset(&s->ctr, 0, sizeof(s->ctr));
     s->ev_used = 0;
     s->kept.valid = false;
-    s->ctr.n_psm = in->n_psm; s->ctr.n_spec = in->n_spec;
-    if (in->n_psm == 0) return PA_OK;
+    s->ctr.n_psm = p_hi - p_lo; s->ctr.n_spec = in->n_spec;
+    if (p_hi == p_lo) return PA_OK;
     const bool in_dev = is_device_ptr(in->mz);
     const bool out_dev = is_device_ptr(out->best_score ? (void*)out->best_score
                                        : out->best_sig ? (void*)out->best_sig
                                        : out->ascores ? (void*)out->ascores : (void*)out->psm_status);
     const bool keep = (flags & PA_KEEP_ISOFORMS) != 0;
+    const int64_t n_range = p_hi - p_lo;
     for (int i = 0; i < 2; i++) {
         CK(s->slot[i].lookups.ensure(8));
         CK(cudaMemsetAsync(s->slot[i].lookups.p, 0, 8, s->slot[i].st));
@@ -975,69 +1021,79 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
     if (in_dev) {
         // Device-resident batch: PA_DEV_CHUNKS chunks that alternate between the two streams (see the note at
         // PA_DEV_CHUNKS: one by default).  One small kernel gathers every range end the host needs, a second
-        // checks that psm_spec is non-decreasing (cutting on PSM indices relies on it), a third finds the
-        // largest spectrum: one device -> host copy instead of one per value.
-        int C = keep ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(PA_DEV_CHUNKS, in->n_psm / PA_DEV_CHUNK_MIN));
-        const int64_t per = (in->n_psm + C - 1) / C;
+        // checks the CSR arrays (and that psm_spec is non-decreasing: cutting on PSM indices relies on it), a
+        // third finds the largest spectrum: one device -> host copy instead of one per value.
+        int C = keep ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(PA_DEV_CHUNKS, n_range / PA_DEV_CHUNK_MIN));
+        const int64_t per = (n_range + C - 1) / C;
         DevBuf& tb = s->slot[0].totals;
         CK(tb.ensure(sizeof(PlanTotals) + sizeof(DevBounds)));
         DevBounds* d_b = (DevBounds*)tb.p;
         CK(cudaMemset(d_b, 0, sizeof(DevBounds)));
-        k_dev_bounds<<<1, 32>>>(in->spec_off, in->psm_spec, in->pep_off, in->mod_off, in->n_psm, in->n_spec, C, per, d_b);
-        k_check_psm_spec<<<(unsigned)std::min<int64_t>((in->n_psm + 255) / 256, 1184), 256>>>(in->psm_spec, in->n_psm, in->n_spec, &d_b->bad);
+        k_dev_bounds<<<1, 32>>>(in->spec_off, in->psm_spec, in->pep_off, in->aux_off, in->mod_off, p_lo, p_hi, in->n_spec, C, per, d_b);
+        k_check_batch<<<(unsigned)std::min<int64_t>((std::max(n_range, in->n_spec) + 255) / 256, 1184), 256>>>(
+            in->psm_spec, in->pep_off, in->aux_off, in->n_mod, in->mod_off, in->spec_off, p_lo, p_hi, in->n_spec, &d_b->bad);
         k_max_peaks<<<(unsigned)((in->n_spec + 255) / 256), 256>>>(in->spec_off, in->n_spec, &d_b->max_peaks);
         CK(cudaGetLastError());
         s->ctr.kernel_launches += 3;
         DevBounds hb;
         CK(cudaMemcpy(&hb, d_b, sizeof(DevBounds), cudaMemcpyDeviceToHost));
+        if (hb.bad & 2) return fail(s, PA_ERR_ARG, "inconsistent batch: an offset array is not a non-decreasing CSR index or mod_off does not follow n_mod");
+        if (hb.n_aux > 0 && (!in->aux_pos || !in->aux_mass)) return fail(s, PA_ERR_ARG, "aux_off is not empty but aux_pos / aux_mass is NULL");
         dev_max_peaks = hb.max_peaks;
-        if (hb.bad) C = 1;                       // unordered PSM -> spectrum map: one chunk over everything
+        const bool unordered = (hb.bad & 1) != 0;
+        if (unordered) C = 1;                    // unordered PSM -> spectrum map: one chunk over everything
         for (int c = 0; c < C; c++) {
             const int a = (C == 1) ? 0 : c, z = (C == 1) ? hb.n : c + 1;       // boundary indices
-            ChunkRange r = {hb.p[a], hb.p[z], hb.bad ? 0 : hb.s0[a], hb.bad ? in->n_spec : hb.s1[z]};
+            ChunkRange r = {hb.p[a], hb.p[z], unordered ? 0 : hb.s0[a], unordered ? in->n_spec : hb.s1[z]};
             if (r.p1 <= r.p0) continue;
             chunks.push_back(r);
             ChunkEnds e;
-            if (hb.bad) {
-                int64_t pk[2]; int32_t pe[2];
+            if (unordered) {
+                int64_t pk[2];
                 CK(cudaMemcpy(&pk[0], in->spec_off, 8, cudaMemcpyDeviceToHost));
                 CK(cudaMemcpy(&pk[1], in->spec_off + in->n_spec, 8, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(&pe[0], in->pep_off, 4, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(&pe[1], in->pep_off + in->n_psm, 4, cudaMemcpyDeviceToHost));
-                e = {pk[0], pk[1], pe[0], pe[1]};
+                e = {pk[0], pk[1], hb.pep[a], hb.pep[z]};
             } else e = {hb.peak0[a], hb.peak1[z], hb.pep[a], hb.pep[z]};
             ends_dev.push_back(e);
             mod_lo.push_back(hb.mod[a]); mod_hi.push_back(hb.mod[z]);
             chunk_maxp.push_back(dev_max_peaks);
+            s->ctr.n_peaks += e.peak_hi - e.peak_lo;
         }
-    } else if (keep) {
-        chunks.push_back({0, in->n_psm, 0, in->n_spec});
     } else {
         bool mono = true;
-        for (int64_t p = 1; p < in->n_psm && mono; p++) mono = in->psm_spec[p] >= in->psm_spec[p - 1];
-        for (int64_t p = 0; p < in->n_psm && mono; p++) mono = in->psm_spec[p] >= 0 && in->psm_spec[p] < in->n_spec;
-        if (!mono) chunks.push_back({0, in->n_psm, 0, in->n_spec});
+        for (int64_t p = p_lo + 1; p < p_hi && mono; p++) mono = in->psm_spec[p] >= in->psm_spec[p - 1];
+        for (int64_t p = p_lo; p < p_hi && mono; p++) mono = in->psm_spec[p] >= 0 && in->psm_spec[p] < in->n_spec;
+        if (!mono || keep) chunks.push_back({p_lo, p_hi, mono ? (int64_t)in->psm_spec[p_lo] : 0, mono ? (int64_t)in->psm_spec[p_hi - 1] + 1 : in->n_spec});
         else {
-            int64_t p0 = 0;
-            while (p0 < in->n_psm) {
+            int64_t p0 = p_lo;
+            while (p0 < p_hi) {
                 int64_t s0 = in->psm_spec[p0];
                 // PSMs sharing the spectrum of p0 that were cut off by the previous chunk stay reachable:
                 // chunk spectra start at the first spectrum referenced
-                int64_t p1 = std::min<int64_t>(p0 + PA_CHUNK_PSM, in->n_psm);
+                int64_t p1 = std::min<int64_t>(p0 + PA_CHUNK_PSM, p_hi);
                 while (p1 > p0 + 1 && in->spec_off[in->psm_spec[p1 - 1] + 1] - in->spec_off[s0] > PA_CHUNK_PEAKS) p1 = p0 + (p1 - p0) / 2;
                 int64_t s1 = (int64_t)in->psm_spec[p1 - 1] + 1;
                 chunks.push_back({p0, p1, s0, s1});
                 p0 = p1;
             }
         }
-    }
-    if (!in_dev)
+        if (!mono) {        // spectrum indices were not validated by the scan above: the plan kernel flags them per PSM
+            const char* why = check_host_range(in, p_lo, p_hi, 0, in->n_spec);
+            if (why) return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why);
+        }
         for (auto& c : chunks) {
+            if (mono) {
+                const char* why = (&c == &chunks[0]) ? check_host_range(in, c.p0, c.p1, c.s0, c.s1) : nullptr;
+                if (why) return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why);
+            }
             int64_t m = 0;
             for (int64_t q = c.s0; q < c.s1; q++) m = std::max<int64_t>(m, in->spec_off[q + 1] - in->spec_off[q]);
-            chunk_maxp.push_back((int)std::min<int64_t>(m, 1 << 20));
+            chunk_maxp.push_back((int)std::min<int64_t>(std::max<int64_t>(m, 0), 1 << 20));
             mod_lo.push_back(in->mod_off[c.p0]); mod_hi.push_back(in->mod_off[c.p1]);
+            s->ctr.n_peaks += in->spec_off[c.s1] - in->spec_off[c.s0];
         }
+    }
+    const bool check_chunks = !in_dev && chunks.size() > 1;      // chunk 0 was checked above
 
     // ---- two-slot software pipeline ----
     std::vector<ChunkState> cs(chunks.size());
@@ -1047,6 +1103,11 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
     if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
     for (size_t c = 0; c < chunks.size(); c++) {
         if (c + 1 < chunks.size()) {
+            if (check_chunks) {
+                const ChunkRange& n = chunks[c + 1];
+                const char* why = check_host_range(in, n.p0, n.p1, n.s0, n.s1);
+                if (why) { cudaDeviceSynchronize(); return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why); }
+            }
             // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
             rc = chunk_front(s, (int)((c + 1) & 1), in, in_dev, chunks[c + 1], mod_lo[c + 1], mod_hi[c + 1],
                              chunk_maxp[c + 1], cs[c + 1], in_dev ? &ends_dev[c + 1] : nullptr);
@@ -1072,8 +1133,61 @@ extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results
     }
     cudaEventElapsedTime(&s->ctr.ms_total, e_all0, e_all1);
     s->ctr.n_fragment_lookups = (int64_t)(*s->slot[0].h_lookups) + (int64_t)(*s->slot[1].h_lookups);
-    if (!in_dev) s->ctr.n_peaks = in->spec_off[in->n_spec] - in->spec_off[0];
     return PA_OK;
+}
+
+static int busy_error(pa_scorer* s) { return fail(s, PA_ERR_STATE, "an asynchronous pa_score_batch_async call is in flight: call pa_wait first"); }
+
+extern "C" int pa_score_batch(pa_scorer* s, const pa_batch* in, const pa_results* out, uint32_t flags) {
+    if (!s) return PA_ERR_ARG;
+    if (s->busy) return busy_error(s);
+    return score_impl(s, in, out, 0, in ? in->n_psm : 0, flags);
+}
+
+extern "C" int pa_score_range(pa_scorer* s, const pa_batch* in, const pa_results* out, int64_t psm_lo, int64_t psm_hi,
+                              uint32_t flags) {
+    if (!s) return PA_ERR_ARG;
+    if (s->busy) return busy_error(s);
+    return score_impl(s, in, out, psm_lo, psm_hi, flags);
+}
+
+// The path has one host decision per chunk (the plan totals size the isoform scratch), so "asynchronous" means a
+// host thread owned by the scorer runs the same orchestration while the caller goes on; the caller's stream
+// (if any) is honoured as a dependency: work queued on it before this call completes before the inputs are read.
+extern "C" int pa_score_batch_async(pa_scorer* s, const pa_batch* in, const pa_results* out, int64_t psm_lo,
+                                    int64_t psm_hi, uint32_t flags, void* stream) {
+    if (!s) return PA_ERR_ARG;
+    if (!in || !out) return fail(s, PA_ERR_ARG, "NULL batch or results");
+    if (s->busy) return busy_error(s);
+    CK(cudaSetDevice(s->device));
+    if (stream) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(ev, (cudaStream_t)stream));
+        for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(s->slot[i].st, ev, 0));
+        CK(cudaEventDestroy(ev));
+    }
+    s->async_in = *in; s->async_out = *out;
+    if (psm_hi < 0) psm_hi = in->n_psm;
+    s->busy = true;
+    s->async_rc = PA_OK;
+    try {
+        s->worker = std::thread([s, psm_lo, psm_hi, flags]() {
+            s->async_rc = score_impl(s, &s->async_in, &s->async_out, psm_lo, psm_hi, flags);
+        });
+    } catch (...) {
+        s->busy = false;
+        return fail(s, PA_ERR_STATE, "could not start the orchestration thread");
+    }
+    return PA_OK;
+}
+
+extern "C" int pa_wait(pa_scorer* s) {
+    if (!s) return PA_ERR_ARG;
+    if (!s->busy) return PA_OK;
+    if (s->worker.joinable()) s->worker.join();
+    s->busy = false;
+    return s->async_rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1091,7 +1205,7 @@ extern "C" int64_t pa_fetch_pep_scores(pa_scorer* s, int64_t psm, int64_t cap, u
     CK(cudaMemcpy(&k, s->kept.b.n_mod + q, 4, cudaMemcpyDeviceToHost));
     const int64_t I = off[1] - off[0];
     if (I <= 0 || status != PA_PSM_OK) return 0;
-    DevBuf d_sig, d_cnt, d_sc, d_w, d_tot;
+    TmpBuf d_sig, d_cnt, d_sc, d_w, d_tot;
     CK(d_sig.ensure(I * 8)); CK(d_cnt.ensure(I * PA_N_TOP * 4)); CK(d_sc.ensure(I * PA_N_TOP * 4));
     CK(d_w.ensure(I * 4)); CK(d_tot.ensure(I * 4));
     k_export_psm<<<(unsigned)((I + 127) / 128), 128>>>(s->cfg, off[0], I, S, k, s->kept.iso, d_sig.as<uint64_t>(),
@@ -1138,7 +1252,7 @@ extern "C" int pa_calculate_ambiguity(pa_scorer* s, int64_t psm, uint64_t sig_a,
     PaAmbArgs a;
     a.psm = psm - s->kept.psm_lo; a.sigA = sig_a; a.sigB = sig_b; a.wA = weighted_a; a.wB = weighted_b;
     memcpy(a.scA, scores_a, sizeof(a.scA)); memcpy(a.scB, scores_b, sizeof(a.scB));
-    DevBuf d_out, d_lists;
+    TmpBuf d_out, d_lists;
     CK(d_out.ensure(4));
     a.list_stride = 32;
     while (a.list_stride < s->kept.max_list) a.list_stride <<= 1;
@@ -1149,6 +1263,63 @@ extern "C" int pa_calculate_ambiguity(pa_scorer* s, int64_t psm, uint64_t sig_a,
     CK(cudaMemcpy(out, d_out.p, 4, cudaMemcpyDeviceToHost));
     d_out.release(); d_lists.release();
     return PA_OK;
+}
+
+// ---- sharding over the GPUs of one box --------------------------------------
+// PSMs are independent, so a batch shards with no collective: every GPU takes a contiguous PSM range cut where
+// psm_spec changes (one spectrum is binned by exactly one GPU).  Ranges are balanced by estimated cost, not by
+// count: isoforms x fragments per isoform for the scoring kernels plus `peak_weight` x the spectrum's peaks (shared
+// between the hits of a spectrum) for binning and, with host inputs, the host -> device copy that dominates there.
+// The estimate is taken on a strided sample (<= 32768 PSMs), so the call costs about a millisecond.
+extern "C" int pa_shard_ranges_for(const char* mod_group_c, int32_t n_types_in, int32_t nvar_in, const pa_batch* in,
+                                   int32_t world, double peak_weight, int64_t* cuts) {
+    if (!mod_group_c || !in || !cuts || world < 1) return PA_ERR_ARG;
+    const std::string mod_group(mod_group_c);
+    const int64_t n = in->n_psm;
+    for (int r = 0; r <= world; r++) cuts[r] = (r == world) ? n : 0;
+    if (n <= 0 || world == 1) return PA_OK;
+    if (!in->spec_off || !in->psm_spec || !in->pep_off || !in->pep || !in->n_mod || !in->max_charge) return PA_ERR_ARG;
+    if (is_device_ptr(in->psm_spec)) return PA_ERR_ARG;          // host batches only
+    bool is_site[256] = {false};
+    for (char ch : mod_group) if (ch >= 'A' && ch <= 'Z') is_site[(unsigned char)ch] = true;
+    const bool term_n = mod_group.find('n') != std::string::npos, term_c = mod_group.find('c') != std::string::npos;
+    const int n_types = std::max<int>(1, n_types_in);
+    const int nvar = std::max(1, nvar_in);
+    const int64_t stride = std::max<int64_t>(1, n / 32768);
+    const int64_t m = (n + stride - 1) / stride;
+    std::vector<double> cum(m + 1, 0.);
+    for (int64_t i = 0; i < m; i++) {
+        const int64_t p = i * stride;
+        const int32_t sp = in->psm_spec[p];
+        if (sp < 0 || sp >= in->n_spec || (p > 0 && in->psm_spec[p] < in->psm_spec[p - stride])) return PA_ERR_ARG;   // needs scan-sorted PSMs
+        const int a = in->pep_off[p], L = in->pep_off[p + 1] - a;
+        int S = 0;
+        for (int j = 0; j < L; j++) S += is_site[in->pep[a + j]] || (term_n && j == 0) || (term_c && j == L - 1);
+        const int k = in->n_mod[p];
+        double iso = 0.;
+        if (k >= 0 && k <= S) { iso = 1.; for (int j = 0; j < std::min(k, S - k); j++) iso = iso * (S - j) / (j + 1); }
+        const double frag = (double)n_types * std::max(L - 1, 1) * std::max(in->max_charge[p], 1) * (nvar > 1 ? 0.5 * (nvar + 1) : 1.);
+        // hits of the spectrum: neighbours with the same spectrum index
+        int hits = 1;
+        for (int64_t q = p - 1; q >= 0 && in->psm_spec[q] == sp && hits < 64; q--) hits++;
+        for (int64_t q = p + 1; q < n && in->psm_spec[q] == sp && hits < 64; q++) hits++;
+        const double peaks = (double)(in->spec_off[sp + 1] - in->spec_off[sp]);
+        cum[i + 1] = cum[i] + iso * frag + peak_weight * peaks / hits + 64.;
+    }
+    for (int r = 1; r < world; r++) {
+        const double target = cum[m] * r / world;
+        int64_t i = std::lower_bound(cum.begin(), cum.end(), target) - cum.begin();
+        int64_t p = std::min<int64_t>(std::max<int64_t>(i, 0) * stride, n);
+        p = std::max(p, cuts[r - 1]);
+        while (p > 0 && p < n && in->psm_spec[p] == in->psm_spec[p - 1]) p++;      // never split a spectrum
+        cuts[r] = p;
+    }
+    return PA_OK;
+}
+
+extern "C" int pa_shard_ranges(const pa_scorer* s, const pa_batch* in, int32_t world, double peak_weight, int64_t* cuts) {
+    if (!s) return PA_ERR_ARG;
+    return pa_shard_ranges_for(s->mod_group.c_str(), (int32_t)s->frag_types.size(), s->cfg.nvar_cap, in, world, peak_weight, cuts);
 }
 
 // cpp/ModifiedPeptide.cpp:184-193
@@ -1214,7 +1385,7 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     CK(sl.rcount.ensure((size_t)n_spec * 4));
     CK(sl.ctab.ensure((size_t)n_spec * PA_NCELL)); CK(sl.chead.ensure((size_t)n_spec * sizeof(float2)));
     const bool extra = out_index || out_bin || out_bounds;
-    DevBuf d_index, d_bin, d_bounds;
+    TmpBuf d_index, d_bin, d_bounds;
     if (extra) { CK(d_index.ensure(npk1 * 4)); CK(d_bin.ensure(npk1 * 4)); CK(d_bounds.ensure((size_t)n_spec * 12)); }
     int64_t m = 0;
     for (int64_t q = 0; q < n_spec; q++) m = std::max<int64_t>(m, spec_off[q + 1] - spec_off[q]);
@@ -1252,7 +1423,7 @@ extern "C" int pa_bin_spectra(pa_scorer* s, int64_t n_spec, const int64_t* spec_
 // ---- single-peptide probes ------------------------------------------------------------------------
 // One peptide (+ fixed mods) staged as a 1-PSM chunk without a spectrum, for the probe kernels.
 struct ProbePsm {
-    DevBuf buf;
+    TmpBuf buf;
     PaBatchDev b;
 };
 
@@ -1264,8 +1435,6 @@ static int stage_probe_psm(pa_scorer* s, const uint8_t* pep, int32_t len, const 
             return fail(s, PA_ERR_ARG, "unknown residue letter '%c'", pep[i]);
     for (int a = 0; a < n_aux; a++)
         if (aux_pos[a] > (uint32_t)len) return fail(s, PA_ERR_ARG, "fixed-mod position %u beyond the peptide", aux_pos[a]);
-    int rc = refresh_config(s);
-    if (rc != PA_OK) return rc;
     // layout: pep_off i32[2] | n_mod i32 | max_charge i32 | aux_off i32[2] | psm_spec i32 | pad | aux_pos | aux_mass | pep
     const size_t n_aux1 = (size_t)std::max(n_aux, 1);
     std::vector<unsigned char> h(32 + n_aux1 * 8 + (size_t)len + 8, 0);
@@ -1294,7 +1463,7 @@ extern "C" int pa_fragment_table(pa_scorer* s, const uint8_t* pep, int32_t len, 
     ProbePsm pp;
     int rc = stage_probe_psm(s, pep, len, aux_pos, aux_mass, n_aux, std::max(charge, 1), pp);
     if (rc != PA_OK) return rc;
-    DevBuf d_mz, d_nv;
+    TmpBuf d_mz, d_nv;
     CK(d_mz.ensure((size_t)len * 16 * 4)); CK(d_nv.ensure((size_t)len * 4));
     CK(cudaMemset(d_mz.p, 0, (size_t)len * 16 * 4));
     PaFragArgs a;
@@ -1324,7 +1493,7 @@ extern "C" int pa_site_determining_ions(pa_scorer* s, const uint8_t* pep, int32_
     a.sig_a = sig_a; a.sig_b = sig_b; a.type = fragment_type; a.max_charge = max_charge;
     a.list_stride = 32;
     while (a.list_stride < per_type) a.list_stride <<= 1;
-    DevBuf d_a, d_b, d_cnt, d_lists;
+    TmpBuf d_a, d_b, d_cnt, d_lists;
     CK(d_a.ensure((size_t)a.list_stride * 4)); CK(d_b.ensure((size_t)a.list_stride * 4)); CK(d_cnt.ensure(8));
     if (per_type > PA_LCAP) CK(d_lists.ensure((size_t)4 * a.list_stride * sizeof(float)));
     a.out_a = d_a.as<float>(); a.out_b = d_b.as<float>(); a.counts = d_cnt.as<int32_t>(); a.g_lists = d_lists.as<float>();
@@ -1356,7 +1525,7 @@ extern "C" int pa_log_math(pa_scorer* s, int32_t op, int32_t n, const float* x, 
     std::vector<double> logd(max_tr + 2);
     logd[0] = 0.;
     for (int m = 1; m <= max_tr + 1; m++) logd[m] = std::log((double)m);
-    DevBuf d_in0, d_in1, d_logd, d_out;
+    TmpBuf d_in0, d_in1, d_logd, d_out;
     CK(d_in0.ensure((size_t)n * 4)); CK(d_in1.ensure((size_t)n * 4)); CK(d_out.ensure((size_t)n * 4));
     CK(d_logd.ensure(logd.size() * 8));
     CK(cudaMemcpy(d_in0.p, op == 0 ? (const void*)x : (const void*)k, (size_t)n * 4, cudaMemcpyHostToDevice));
