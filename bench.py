@@ -101,7 +101,10 @@ def cpu_kind():
 
 def cpu_throughput(workload, batch, n_sample, cores):
     """PSMs/s of the CPU reference over the first n_sample PSMs, `cores` forked workers, one
-    scorer object each (the reference is single-threaded and stateful: SURVEY.md section 2.4)"""
+    scorer object each (the reference is single-threaded and stateful: SURVEY.md section 2.4).
+    The rate is taken over the SCORING time of the slowest worker (each worker times its own
+    score_batch call): starting the pool and pickling the sub-batches to the workers is test
+    plumbing, not the reference's work.  The whole-pool wall time is returned too."""
     import multiprocessing as mp
     w = synth.WORKLOADS[workload]
     kind = cpu_kind()
@@ -117,12 +120,36 @@ def cpu_throughput(workload, batch, n_sample, cores):
     t0 = time.perf_counter()
     if cores > 1 and len(jobs) > 1:
         with mp.get_context("fork").Pool(min(cores, len(jobs))) as pool:
-            pool.map(_cpu_worker, jobs)
+            times = pool.map(_cpu_worker, jobs)
+        # more jobs than workers: a worker scores ceil(jobs / workers) sub-batches one after the other
+        rounds = -(-len(jobs) // min(cores, len(jobs)))
+        busy = max(times) * rounds
     else:
-        for j in jobs:
-            _cpu_worker(j)
-    dt = time.perf_counter() - t0
-    return n_sample / dt, kind, n_sample, dt
+        times = [_cpu_worker(j) for j in jobs]
+        busy = sum(times)
+    wall = time.perf_counter() - t0
+    return n_sample / busy, kind, n_sample, busy, wall
+
+
+def cpu_single_call(n_rep=3):
+    """seconds per PyAscore.score call of the compiled reference on the 31 fixture PSMs, one at a time -- the
+    only thing the reference itself times (test/test_ascore.py:20-36)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _golden
+    from oracle import cscorer
+    kind = cpu_kind()
+    cls = cscorer.RefPyAscore if kind == "reference" else cscorer.OraclePyAscore
+    meta, batch, _ = _golden.load("fixtures_by_05")
+    sc = cls(**meta["scorer"])
+    n = batch["n_mod"].size
+    views = [synth.psm_view(batch, i) for i in range(n)]
+    best = float("inf")
+    for _ in range(n_rep + 1):
+        t0 = time.perf_counter()
+        for v in views:
+            sc.score(*v)
+        best = min(best, (time.perf_counter() - t0) / n)
+    return {"us_per_call": best * 1e6, "kind": kind, "psms": int(n)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -175,10 +202,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def bind_near_gpu(index):
-    """Best effort: run this rank (and the pinned buffers it allocates: first touch) on the CPUs of the NUMA
-    node its GPU hangs off, so that the end-to-end leg does not cross the socket interconnect.  Returns a
-    short description for the JSON line; does nothing when the topology is not visible."""
+def _cpu_set(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        x, _, y = part.partition("-")
+        cpus.update(range(int(x), int(y or x) + 1))
+    return cpus
+
+
+def gpu_cpu_affinity(index):
+    """CPUs next to GPU `index`: /sys numa_node of its PCI function, else the "CPU Affinity" column of
+    `nvidia-smi topo -m` (containers often hide the sysfs node).  -> (set of cpus, how) or (None, why)"""
     try:
         r = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
                            capture_output=True, text=True, timeout=20)
@@ -186,19 +223,58 @@ def bind_near_gpu(index):
         if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
             bus = bus[4:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
-        if node < 0:
-            return "numa node not reported"
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
+        if node >= 0:
+            return _cpu_set(open("/sys/devices/system/node/node%d/cpulist" % node).read()), "sysfs numa node %d" % node
+    except Exception:
+        pass
+    try:
+        r = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=30)
+        lines = [l for l in r.stdout.splitlines() if l.strip()]
+        head = next(l for l in lines if "CPU Affinity" in l)
+        cols = [c.strip() for c in head.split("\t")]
+        ci = cols.index("CPU Affinity")
+        row = next(l for l in lines if l.startswith("GPU%d\t" % index) or l.startswith("GPU%d " % index))
+        cells = [c.strip() for c in row.split("\t")]
+        # the header row starts with an empty cell for the row labels
+        cell = cells[ci] if len(cells) > ci else ""
+        if cell and cell[0].isdigit():
+            numa = cells[ci + 1] if len(cells) > ci + 1 else "?"
+            return _cpu_set(cell), "nvidia-smi topo cpu affinity %s (numa %s)" % (cell, numa)
+        return None, "nvidia-smi topo reports no cpu affinity"
+    except Exception as e:
+        return None, "topology not visible (%s)" % type(e).__name__
+
+
+def bind_near_gpu(index):
+    """Best effort: run this rank (and the pinned buffers it allocates: first touch) on the CPUs next to its GPU,
+    so that the end-to-end leg does not cross the socket interconnect.  Returns a description for the JSON line."""
+    cpus, how = gpu_cpu_affinity(index)
+    if cpus is None:
+        return "not bound: " + how
+    try:
         cpus &= os.sched_getaffinity(0)
         if len(cpus) < 2:
-            return "numa node %d has no usable cpus" % node
+            return "not bound: %s has no usable cpus in this container" % how
         os.sched_setaffinity(0, cpus)
-        return "bound to numa node %d (%d cpus)" % (node, len(cpus))
+        return "bound to %d cpus: %s" % (len(cpus), how)
     except Exception as e:
         return "not bound (%s)" % type(e).__name__
+
+
+def set_interleave(on):
+    """MPOL_INTERLEAVE over every memory node for the pages this thread allocates next (the one-process sharded
+    leg pins ONE batch that all GPUs read), or back to the default policy.  Best effort; returns a note."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if len(nodes) < 2:
+            return "single memory node"
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+        rc = libc.syscall(238, 3 if on else 0, ctypes.byref(mask) if on else None, 64 if on else 0)   # set_mempolicy
+        return ("interleaved over nodes %s" % nodes) if rc == 0 and on else ("default policy" if rc == 0 else "set_mempolicy failed (errno %d)" % ctypes.get_errno())
+    except Exception as e:
+        return "not set (%s)" % type(e).__name__
 
 
 def retained_peaks(batch, bin_size, n_top, n_sample=2000):
@@ -225,6 +301,67 @@ def algorithmic_bytes(batch, res_mod_total):
     return 16 * peaks + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 24 * n + 16 * n + 12 * res_mod_total
 
 
+KERNELS = ("bin_topn", "count_score", "select", "ascore")
+CONFIG_NO = {"lowres_phospho": 2, "hires_phospho_nl": 3, "stress": 4, "acetyl_k": 5}
+DEFAULT_PSMS = {"lowres_phospho": 1000000, "hires_phospho_nl": 1000000, "stress": 1024, "acetyl_k": 999999}
+
+
+def kernel_ms(ctr):
+    return {"bin_topn": ctr["ms_bin"], "plan+scan": ctr["ms_plan"], "count_score": ctr["ms_count"],
+            "select": ctr["ms_select"], "ascore": ctr["ms_ascore"]}
+
+
+def roofline_of(workload, batch, mod_total, ctr, peak, peak_src, clocks, sm_count):
+    """`roofline` object of one workload from the counters of a device-resident pass.
+
+    achieved = SURVEY 8(d) algorithmic bytes of the PSMs one launch of the dominant kernel processes / that
+    launch's CUDA-event duration.  The bytes the kernel itself is designed to move (its own reads + writes,
+    intermediates included) are reported beside it as `kernel_bytes`, the ncu-measured DRAM traffic as `traffic`."""
+    w = synth.WORKLOADS[workload]
+    n_psm = int(batch["n_mod"].size)
+    kern = kernel_ms(ctr)
+    dom = max(KERNELS, key=lambda k: kern[k])
+    n_launch = max(int(ctr["n_chunks"]), 1)          # every stage launches once per chunk of the batch
+    peaks_n = int(batch["spec_off"][-1])
+    n_spec = batch["spec_off"].size - 1
+    hits = w["hits"]
+    retained = 8 * retained_peaks(batch, w["scorer"]["bin_size"], w["scorer"]["n_top"])
+    index = 268 * n_spec
+    pep_b, aux_b, n_iso = int(batch["pep_off"][-1]), 8 * int(batch["aux_off"][-1]), int(ctr["n_isoforms"])
+    own = {"bin_topn": 16 * peaks_n + retained + index,
+           "count_score": (retained + index) * hits + pep_b + aux_b + 12 * n_psm + 24 * n_iso,
+           "select": 4 * n_iso + 28 * n_psm + pep_b + 26 * mod_total,
+           "ascore": (retained + index) * hits + pep_b + aux_b + 20 * mod_total}
+    step_alg = algorithmic_bytes(batch, mod_total)
+    dom_ms = kern[dom] / n_launch
+    achieved = step_alg / n_launch / (dom_ms * 1e-3) / 1e9
+    traffic = issue = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+        traffic = tj[dom]["dram_bytes_per_psm"] * n_psm / n_launch
+        mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+        ipeak = sm_count * 4 * mhz * 1e6
+        iach = tj[dom]["warp_inst_per_psm"] * n_psm / (kern[dom] * 1e-3)
+        issue = {"achieved": iach, "peak": ipeak, "unit": "warp-inst/s", "frac": iach / ipeak,
+                 "warp_inst_per_psm": tj[dom]["warp_inst_per_psm"], "measured_in_this_run": False,
+                 "source": "BORROWED: instruction count per PSM from the committed ncu capture (profiles/traffic.json), "
+                           "an earlier build; only the kernel time is this run's.  Says the SMs are busy, not that the "
+                           "work is minimal"}
+    except Exception:
+        pass
+    kms = sum(kern.values())
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": step_alg / n_launch, "launch_ms": dom_ms,
+            "kernel_bytes": {"per_launch": own[dom] / n_launch, "achieved": own[dom] / n_launch / (dom_ms * 1e-3) / 1e9,
+                             "frac": own[dom] / n_launch / (dom_ms * 1e-3) / 1e9 / peak,
+                             "note": "the dominant kernel's own reads + writes (its intermediates included), not the 8(d) figure"},
+            "note": "path is issue/latency bound, not HBM bound (DESIGN.md); frac = SURVEY 8(d) bytes / dominant kernel time / HBM copy peak",
+            "issue": issue,
+            "step": {"algorithmic_bytes": step_alg, "kernel_ms": kms, "achieved": step_alg / (kms * 1e-3) / 1e9,
+                     "frac": step_alg / (kms * 1e-3) / 1e9 / peak}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -237,6 +374,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (other BASELINE configs, sharded config 3)")
+    ap.add_argument("--configs-psms", type=int, default=0, help="PSMs of the sharded config-3 dataset (default 1M)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -244,13 +383,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    default_psms = {"lowres_phospho": 1000000, "hires_phospho_nl": 1000000, "stress": 1024, "acetyl_k": 999999}
-    n_psm = args.psms or default_psms[args.workload]
+    n_psm = args.psms or DEFAULT_PSMS[args.workload]
     cores = os.cpu_count() or 1
     w = synth.WORKLOADS[args.workload]
     cfg = {"workload": "%s: %d synthetic PSMs/GPU/step (BASELINE config %s), seed %d" % (
-        args.workload, n_psm, {"lowres_phospho": 2, "hires_phospho_nl": 3, "stress": 4, "acetyl_k": 5}[args.workload],
-        args.seed), "scorer": w["scorer"], "neutral_losses": w["neutral_losses"], "psms_per_gpu": n_psm,
+        args.workload, n_psm, CONFIG_NO[args.workload], args.seed), "scorer": w["scorer"],
+        "neutral_losses": w["neutral_losses"], "psms_per_gpu": n_psm,
         "l2": "inputs (>= 4 GB per step at the default size) exceed the 126 MB L2; no flush needed"}
 
     # ------------------------------------------------------------------ reference arm
@@ -261,18 +399,21 @@ def main():
         batch = generate(args.workload, min(per_step, n_psm), args.seed, cores)
         vals = []
         for i in range(args.warmup + args.steps):
-            v, kind, ns, dt = cpu_throughput(args.workload, batch, per_step, cores)
+            v, kind, ns, busy, wall = cpu_throughput(args.workload, batch, per_step, cores)
             if i >= args.warmup:
-                vals.append((v, dt))
-        value = float(np.mean([v for v, _ in vals]))
-        ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+                vals.append((v, busy, wall))
+        value = float(np.mean([v for v, _, _ in vals]))
+        ms = float(np.mean([b for _, b, _ in vals]) * 1e3)
         sample = "first %d PSMs of the workload per step, %d forked workers with one scorer each" % (ns, cores)
         print(json.dumps({
             "impl": "reference", "metric": "PSMs scored/sec", "value": value, "unit": "PSM/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": value, "unit": "PSM/s", "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "PSM/s", "cores": cores, "kind": kind, "sample": sample,
+                             "timing": "slowest worker's own scoring time (pool start-up and pickling excluded)",
+                             "value_incl_pool_startup": float(np.mean([ns / wl for _, _, wl in vals]))},
             "e2e": {"value": value, "unit": "PSM/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "single_call": cpu_single_call(),
             "gpu_launches": 0}))
         return
 
@@ -281,15 +422,27 @@ def main():
     procs = max(1, min(cores // world, len(os.sched_getaffinity(0))))
     t0 = time.time()
     batch = generate(args.workload, n_psm, args.seed + 1000 * rank, procs)   # before any CUDA call (fork)
-    gen_s = time.time() - t0
     n_psm = int(batch["n_mod"].size)
+    # the other BASELINE configs (rank 0 only): config 3 is scored at every N as ONE dataset sharded over the N
+    # GPUs (strong scaling); configs 4 and 5 at N = 1
+    extra = {}
+    if rank == 0 and not args.no_configs and args.workload == "lowres_phospho":
+        names = ["hires_phospho_nl"] + (["stress", "acetyl_k"] if world == 1 else [])
+        for nm in names:
+            m = (args.configs_psms or DEFAULT_PSMS[nm]) if nm == "hires_phospho_nl" else DEFAULT_PSMS[nm]
+            if args.psms and nm != "stress":
+                m = min(m, max(args.psms, 4096))
+            extra[nm] = generate(nm, m, args.seed, max(1, len(os.sched_getaffinity(0))))
+    gen_s = time.time() - t0
 
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
+    store = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from pyascore_b200 import Scorer, batch as pb
+        store = dist.distributed_c10d._get_default_store()
+    from pyascore_b200 import MultiScorer, Scorer, batch as pb, shard
 
     def barrier():
         if world > 1:
@@ -303,54 +456,72 @@ def main():
     mod_total = int(batch["mod_off"][-1])
 
     # device-resident copy (value) and pinned host copy (e2e)
-    dev = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda() for k, v in batch.items()}
-    host = pb.pin_batch(batch)
-    out_host = {k: pb.pinned_empty(mod_total if k in ("ascores", "alt_sites") else n_psm, dt)
-                for k, dt in pb._OUT_DTYPES.items()}
+    def to_dev(b, device):
+        return {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).to(device) for k, v in b.items()}
+
     tm = dict(best_sig=torch.int64, best_score=torch.float32, n_iso=torch.int64, n_sites=torch.int32,
               ascores=torch.float32, alt_sites=torch.int64, psm_status=torch.int32)
-    out_dev = {k: torch.empty(max(mod_total if k in ("ascores", "alt_sites") else n_psm, 1), dtype=tm[k], device="cuda")
-               for k in tm}
+
+    def out_dev_for(n, mods, device):
+        return {k: torch.empty(max(mods if k in ("ascores", "alt_sites") else n, 1), dtype=tm[k], device=device) for k in tm}
+
+    def out_host_for(n, mods):
+        return {k: pb.pinned_empty(mods if k in ("ascores", "alt_sites") else n, dt) for k, dt in pb._OUT_DTYPES.items()}
+
+    dev = to_dev(batch, "cuda:%d" % local)
+    host = pb.pin_batch(batch)
+    out_host = out_host_for(n_psm, mod_total)
+    out_dev = out_dev_for(n_psm, mod_total, "cuda:%d" % local)
 
     def run_steps(inputs, outputs, steps):
+        """-> (sum of the library's CUDA-event times, wall seconds around the calls, last counters)"""
         ms = 0.0
         ctr = None
+        t = time.perf_counter()
         for _ in range(steps):
             scorer.score_batch(inputs, out=outputs)
             ctr = scorer.counters()
             ms += ctr["ms_total"]
-        return ms, ctr
+        return ms, time.perf_counter() - t, ctr
 
-    def h2d_peak_gbs(nbytes=1 << 30, reps=4):
-        """plain pinned-host -> device copy rate of this box (what bounds the e2e leg)"""
+    def h2d_gbs(nbytes=1 << 30, reps=4, together=False):
+        """pinned-host -> device copy rate of this rank's GPU; `together`: every rank copies at the same time
+        (after a barrier), which is what the end-to-end leg of an N-rank run is up against"""
         src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
         best = 0.0
         for _ in range(reps):
+            if together:
+                barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); dst.copy_(src, non_blocking=True); e1.record(); torch.cuda.synchronize()
             best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
         return best
 
-    pcie_gbs = h2d_peak_gbs() if not args.no_e2e else None
+    pcie_gbs = pcie_together = None
+    if not args.no_e2e:
+        pcie_gbs = h2d_gbs()
+        if world > 1:
+            mine = torch.tensor([h2d_gbs(together=True)], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            pcie_together = [float(x.item()) for x in allr]
     sampler = ClockSampler(local)
     # ---- value: inputs resident in HBM ----
     run_steps(dev, out_dev, args.warmup)
     barrier()
     sampler.start()
-    t_wall = time.perf_counter()
-    ms_dev, ctr_dev = run_steps(dev, out_dev, args.steps)
+    ms_dev, wall_dev, ctr_dev = run_steps(dev, out_dev, args.steps)
     barrier()
-    wall_dev = time.perf_counter() - t_wall
     # ---- e2e: host buffers through the public API ----
     e2e_steps = 1 if args.no_e2e else args.steps
     run_steps(host, out_host, 1 if args.no_e2e else max(1, min(args.warmup, 2)))
     barrier()
-    t_wall = time.perf_counter()
-    ms_e2e, ctr_e2e = run_steps(host, out_host, e2e_steps)
+    ms_e2e, wall_e2e, ctr_e2e = run_steps(host, out_host, e2e_steps)
     ms_e2e *= args.steps / e2e_steps
+    wall_e2e *= args.steps / e2e_steps
     barrier()
-    wall_e2e = time.perf_counter() - t_wall
     clocks = sampler.stop()
 
     # parity guard: both paths must agree bit for bit, and every PSM must have been scored
@@ -362,81 +533,69 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev_max, ms_e2e_max, wall_dev_ms, wall_e2e_ms = [float(x) for x in t.cpu()]
     total_psm = n_psm * world * args.steps
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+    out = None
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "measured (MEASURED_PEAKS.json)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        kern = {"bin_topn": ctr_dev["ms_bin"], "plan+scan": ctr_dev["ms_plan"], "count_score": ctr_dev["ms_count"],
-                "select": ctr_dev["ms_select"], "ascore": ctr_dev["ms_ascore"]}
-        dom = max(("bin_topn", "count_score", "select", "ascore"), key=lambda k: kern[k])
-        n_launch = {"bin_topn": ctr_dev["launches_bin"], "count_score": ctr_dev["launches_count"],
-                    "select": ctr_dev["launches_select"], "ascore": max(ctr_dev["launches_ascore"] // 2, 1)}[dom]
-        peaks_n = int(batch["spec_off"][-1])
-        # algorithmic bytes of each kernel's own stage per step (DESIGN.md section "kernels")
-        n_spec = batch["spec_off"].size - 1
-        hits = w["hits"]
-        # K1 writes, and K2 / K3b read, 8 B per retained peak plus the 256-cell index, its header and the count
-        retained = 8 * retained_peaks(batch, w["scorer"]["bin_size"], w["scorer"]["n_top"])
-        index = 268 * n_spec
-        alg = {"bin_topn": 16 * peaks_n + retained + index,
-               "count_score": (retained + index) * hits + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 12 * n_psm + 24 * int(ctr_dev["n_isoforms"]),
-               "select": 4 * int(ctr_dev["n_isoforms"]) + 28 * n_psm + int(batch["pep_off"][-1]) + 26 * mod_total,
-               "ascore": (retained + index) * hits + int(batch["pep_off"][-1]) + 8 * int(batch["aux_off"][-1]) + 16 * mod_total + 4 * mod_total}
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per PSM at
-        # 262144 PSMs/launch, profiles/traffic.json), scaled to this run's PSMs per launch
-        traffic = None
-        issue = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj[args.workload][dom]["dram_bytes_per_psm"] * n_psm / max(n_launch, 1)
-            # issue-slot view of the same kernel (the path is bound by warp-instruction issue):
-            # executed warp instructions per PSM from the committed ncu capture x PSMs per launch / the launch
-            # time measured here, against SMs x 4 schedulers x the SM clock sampled during this run
-            props = torch.cuda.get_device_properties(local)
-            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
-            ipeak = props.multi_processor_count * 4 * mhz * 1e6
-            iach = tj[args.workload][dom]["warp_inst_per_psm"] * n_psm / (kern[dom] * 1e-3)
-            all_inst = sum(tj[args.workload][k]["warp_inst_per_psm"] for k in ("bin_topn", "count_score", "select", "ascore"))
-            issue = {"achieved": iach, "peak": ipeak, "unit": "warp-inst/s", "frac": iach / ipeak,
-                     "warp_inst_per_psm": tj[args.workload][dom]["warp_inst_per_psm"],
-                     "step_frac": all_inst * n_psm / (sum(kern[k] for k in ("bin_topn", "count_score", "select", "ascore")) * 1e-3) / ipeak,
-                     "source": "profiles/traffic.json (ncu smsp__inst_executed.sum) x this run's CUDA-event times"}
-        except Exception:
-            pass
-        dom_ms = kern[dom] / max(n_launch, 1)
-        achieved = alg[dom] / max(n_launch, 1) / (dom_ms * 1e-3) / 1e9
-        step_alg = algorithmic_bytes(batch, mod_total)
-        kernel_ms = sum(kern.values())
+        kern = kernel_ms(ctr_dev)
+        h2d_ach = ctr_e2e["bytes_h2d"] / (wall_e2e_ms / args.steps * 1e-3) / 1e9
+        ceiling = min(pcie_together) if pcie_together else pcie_gbs
         out = {
             "metric": "PSMs scored/sec", "value": total_psm / (ms_dev_max * 1e-3), "unit": "PSM/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "clocks": clocks,
-            "e2e": {"value": total_psm / (ms_e2e_max * 1e-3), "unit": "PSM/s",
+            # end to end = wall clock around the public API call (host work of the call included), max over ranks
+            "e2e": {"value": total_psm / (wall_e2e_ms * 1e-3), "unit": "PSM/s",
                     "h2d_bytes_per_step": int(ctr_e2e["bytes_h2d"]), "d2h_bytes_per_step": int(ctr_e2e["bytes_d2h"]),
-                    "ms_per_step": ms_e2e_max / args.steps, "wall_ms_per_step": wall_e2e_ms / args.steps,
-                    "h2d_achieved_gbs": ctr_e2e["bytes_h2d"] / (ms_e2e_max / args.steps * 1e-3) / 1e9,
-                    "h2d_copy_peak_gbs": pcie_gbs,
-                    "note": "bound by the host->device link: h2d_achieved_gbs vs a plain pinned 1 GiB copy on this box"},
+                    "ms_per_step": wall_e2e_ms / args.steps, "timing": "wall clock around Scorer.score_batch, max over ranks",
+                    "ms_per_step_cuda_events": ms_e2e_max / args.steps,
+                    "h2d_achieved_gbs": h2d_ach, "h2d_copy_peak_gbs": pcie_gbs,
+                    "h2d_concurrent_peak_gbs": pcie_together,
+                    "h2d_frac_of_ceiling": (h2d_ach / ceiling) if ceiling else None,
+                    "note": "bound by the host->device link: h2d_achieved_gbs (rank 0's bytes / the slowest rank's time) vs a "
+                            "plain pinned 1 GiB copy alone (h2d_copy_peak_gbs) and with every rank copying at once "
+                            "(h2d_concurrent_peak_gbs, per rank; the ceiling is the slowest)"},
             "gpu_launches": int(ctr_dev["kernel_launches"]) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "path is issue/latency bound, not HBM bound (DESIGN.md); frac is of the HBM copy peak",
-                         "algorithmic_bytes_per_launch": alg[dom] / max(n_launch, 1), "launch_ms": dom_ms,
-                         "issue": issue,
-                         "step": {"algorithmic_bytes": step_alg, "kernel_ms": kernel_ms,
-                                  "achieved": step_alg / (kernel_ms * 1e-3) / 1e9,
-                                  "frac": step_alg / (kernel_ms * 1e-3) / 1e9 / peak}},
+            "roofline": roofline_of(args.workload, batch, mod_total, ctr_dev, peak, peak_src, clocks, sm_count),
             "kernel_ms_per_step": kern, "wall_ms_per_step": wall_dev_ms / args.steps,
             "isoforms_per_step": int(ctr_dev["n_isoforms"]), "fragment_lookups_per_step": int(ctr_dev["n_fragment_lookups"]),
             "host_and_device_paths_bit_identical": bool(same), "psms_not_scored": n_bad, "gen_seconds": gen_s,
             "numa": numa,
         }
+    scorer.close()
+    del dev, host, out_dev, out_host, scorer
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ `configs`: the other BASELINE configs
+    if rank == 0 and extra:
+        try:
+            os.sched_setaffinity(0, range(cores))      # the sharded leg drives every GPU from this process
+        except Exception:
+            pass
+        out["configs"] = {}
+        for nm, xb in extra.items():
+            try:
+                out["configs"][nm] = run_config(nm, xb, world if nm == "hires_phospho_nl" else 1, args, peak, peak_src,
+                                                clocks, sm_count, torch, pb, shard, MultiScorer, to_dev, out_dev_for, out_host_for)
+            except Exception as e:          # a config leg never takes the headline line down
+                out["configs"][nm] = {"error": repr(e)}
+    if world > 1:
+        # ranks > 0 wait on the store (a CPU-side wait: an NCCL barrier would spin on their GPUs while rank 0 uses them)
+        if rank == 0:
+            store.set("configs_done", "1")
+        else:
+            store.wait(["configs_done"])
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            out["single_call"] = gpu_single_call(local)
             # CPU reference on this box's host cores, in a fresh process (no fork after CUDA init)
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
                    "--workload", args.workload, "--seed", str(args.seed), "--psms", str(n_psm)]
@@ -444,14 +603,124 @@ def main():
                 cmd += ["--cpu-sample", str(args.cpu_sample)]
             try:
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-                out["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+                ref = json.loads(r.stdout.strip().splitlines()[-1])
+                out["cpu_baseline"] = ref["cpu_baseline"]
+                out["single_call"]["reference"] = ref.get("single_call")
             except Exception as e:  # the baseline is reported, never required
                 out["cpu_baseline"] = {"value": None, "unit": "PSM/s", "cores": cores, "kind": "unavailable",
                                        "sample": "failed: %r" % (e,)}
         print(json.dumps(out))
-    scorer.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_single_call(device, n_rep=5):
+    """microseconds per drop-in `PyAscore.score` call (a batch of one through the same kernels) on the reference's
+    31 fixture PSMs, results read back -- beside the compiled reference's figure (test/test_ascore.py:20-36)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _golden
+    from pyascore_b200 import PyAscore
+    meta, batch, _ = _golden.load("fixtures_by_05")
+    sc = PyAscore(device=device, **meta["scorer"])
+    n = batch["n_mod"].size
+    views = [synth.psm_view(batch, i) for i in range(n)]
+    views = [(np.ascontiguousarray(v[0]), np.ascontiguousarray(v[1])) + tuple(v[2:5]) +
+             (np.ascontiguousarray(v[5], np.uint32), np.ascontiguousarray(v[6], np.float32)) for v in views]
+    best = float("inf")
+    for _ in range(n_rep + 1):
+        t0 = time.perf_counter()
+        for v in views:
+            sc.score(*v)
+            _ = sc.best_score
+        best = min(best, (time.perf_counter() - t0) / n)
+    return {"us_per_call": best * 1e6, "psms": int(n), "what": "PyAscore.score + best_score on the 31 fixture PSMs, one call each"}
+
+
+def run_config(name, batch, n_dev, args, peak, peak_src, clocks, sm_count, torch, pb, shard, MultiScorer, to_dev,
+               out_dev_for, out_host_for):
+    """One BASELINE config scored as ONE dataset over `n_dev` GPUs from this process: the batch is cut with the
+    library's cutter (pa_shard_ranges: contiguous PSM ranges on spectrum boundaries, balanced by estimated cost), every
+    GPU scores its range and writes its slice of one pinned result.  Reports end to end (pinned host arrays ->
+    pinned results, wall clock) and with every shard resident in its GPU's HBM (wall clock + the slowest GPU's
+    CUDA-event time), plus the kernel split and roofline of GPU 0's shard."""
+    w = synth.WORKLOADS[name]
+    steps, warm = max(2, min(args.steps, 5)), 2
+    pb.add_mod_off(batch)
+    n = int(batch["n_mod"].size)
+    mods = int(batch["mod_off"][-1])
+    policy = set_interleave(True) if n_dev > 1 else "single GPU"
+    host = pb.pin_batch(batch)
+    out_host = out_host_for(n, mods)
+    if n_dev > 1:
+        set_interleave(False)
+    ms = MultiScorer(devices=list(range(n_dev)), **w["scorer"])
+    for g, m in w["neutral_losses"]:
+        ms.add_neutral_loss(g, m)
+
+    def sync_all():
+        for d in range(n_dev):
+            torch.cuda.synchronize(d)
+
+    # ---- end to end through MultiScorer.score_batch (cut + N concurrent ranges) ----
+    for _ in range(warm):
+        ms.score_batch(host, out=out_host)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ms.score_batch(host, out=out_host)
+    e2e_s = (time.perf_counter() - t0) / steps
+    ctrs = ms.counters()
+    ranges = ms.last_ranges
+    h2d = sum(c["bytes_h2d"] for c in ctrs)
+    # ---- every shard resident on its GPU ----
+    shards = [shard.take_shard(batch, a, b) for a, b in ranges]
+    for sb in shards:
+        pb.add_mod_off(sb)
+    devs = [to_dev(sb, "cuda:%d" % d) for d, sb in enumerate(shards)]
+    outs = [out_dev_for(int(sb["n_mod"].size), int(sb["mod_off"][-1]), "cuda:%d" % d) for d, sb in enumerate(shards)]
+
+    def resident_pass():
+        for sc, dv, od in zip(ms.scorers, devs, outs):
+            sc.score_batch_async(dv, out=od)
+        for sc in ms.scorers:
+            sc.wait()
+    for _ in range(3):
+        resident_pass()
+    sync_all()
+    t0 = time.perf_counter()
+    ev = 0.0
+    for _ in range(steps):
+        resident_pass()
+        ev += max(sc.counters()["ms_total"] for sc in ms.scorers)
+    dev_wall_s = (time.perf_counter() - t0) / steps
+    dev_ev_s = ev / steps * 1e-3
+    ctr0 = ms.scorers[0].counters()
+    # sharded result == the same PSMs scored resident (bit for bit), every PSM scored
+    same = True
+    for (a, b), od in zip(ranges, outs):
+        for k in ("best_sig", "best_score", "n_iso", "psm_status"):
+            same &= od[k][:b - a].cpu().numpy().tobytes() == out_host[k][a:b].tobytes()
+        ma, mb = int(batch["mod_off"][a]), int(batch["mod_off"][b])
+        for k in ("ascores", "alt_sites"):
+            same &= od[k][:mb - ma].cpu().numpy().tobytes() == out_host[k][ma:mb].tobytes()
+    res = {
+        "workload": "%s: ONE dataset of %d synthetic PSMs (BASELINE config %d), sharded over %d GPU(s) by pa_shard_ranges" % (
+            name, n, CONFIG_NO[name], n_dev),
+        "scaling": "strong", "n_gpus": n_dev, "psms": n, "steps": steps,
+        "value": n / dev_ev_s, "unit": "PSM/s", "ms_per_step": dev_ev_s * 1e3,
+        "value_timing": "shards resident in HBM; slowest GPU's CUDA-event time per pass", "wall_ms_per_step": dev_wall_s * 1e3,
+        "e2e": {"value": n / e2e_s, "unit": "PSM/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(sum(c["bytes_d2h"] for c in ctrs)), "h2d_achieved_gbs": h2d / e2e_s / 1e9,
+                "timing": "wall clock around MultiScorer.score_batch (cut + every range), one process, pinned host arrays",
+                "pinned_pages": policy},
+        "shard_psms": [b - a for a, b in ranges],
+        "shard_ms_cuda_events": [c["ms_total"] for c in ctrs],
+        "kernel_ms_per_step_gpu0": kernel_ms(ctr0),
+        "roofline_gpu0": roofline_of(name, shards[0], int(shards[0]["mod_off"][-1]), ctr0, peak, peak_src, clocks, sm_count),
+        "sharded_equals_resident_bit_for_bit": bool(same), "psms_not_scored": int((out_host["psm_status"] != 0).sum()),
+    }
+    ms.close()
+    return res
 
 
 if __name__ == "__main__":

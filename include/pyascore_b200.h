@@ -216,6 +216,7 @@ typedef struct {
     float ms_bin, ms_plan, ms_count, ms_select, ms_total; /* CUDA-event times, summed over chunks */
     int64_t launches_bin, launches_count, launches_select, launches_ascore;
     float ms_ascore, reserved;          /* ms_select = best-isoform selection, ms_ascore = Ascore kernels */
+    int64_t n_chunks;                   /* chunks the batch was cut into: every stage launches once per chunk */
 } pa_counters_t;
 
 /* Counters of the last pa_score_batch (roofline arithmetic: SURVEY.md section 8d). */

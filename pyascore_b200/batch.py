@@ -319,7 +319,11 @@ class MultiScorer:
         if n == 1:
             self.last_ranges = [(0, int(batch["n_mod"].shape[0]))]
             return self.scorers[0].score_batch(batch, out=out, want=want)
-        self.last_ranges = ranges = self.scorers[0].shard_ranges(batch, n, peak_weight)
+        try:
+            self.last_ranges = ranges = self.scorers[0].shard_ranges(batch, n, peak_weight)
+        except ValueError:                  # PSMs not in spectrum order: cannot be cut on spectrum boundaries
+            self.last_ranges = [(0, int(batch["n_mod"].shape[0]))]
+            return self.scorers[0].score_batch(batch, out=out, want=want)
         started = []
         err = None
         for sc, r in zip(self.scorers, ranges):

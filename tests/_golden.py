@@ -50,3 +50,39 @@ def rel_close(a, b, tol=1e-6):
     if not np.array_equal(a[~fin], b[~fin], equal_nan=True):
         return False
     return bool(np.all(np.abs(a[fin] - b[fin]) <= tol * np.abs(b[fin])))
+
+
+BIG_DIR = os.path.join(GOLDEN_DIR, "big")
+
+
+def big_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(BIG_DIR, "*.npz")))
+
+
+def load_big(name):
+    """goldens of tests/golden/make_golden_big.py: per-PSM results + SHA-256 of the whole pep_scores table"""
+    z = np.load(os.path.join(BIG_DIR, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    batch = {k[3:]: np.ascontiguousarray(z[k]) for k in z.files if k.startswith("in_")}
+    ref = {k[4:]: z[k] for k in z.files if k.startswith("ref_")}
+    n = batch["n_mod"].size
+    seqs = bytes(ref["best_sequence"]).decode().split("\n")
+    ref["best_sequence"] = (seqs + [""] * n)[:n]
+    ref["table_sha256"] = bytes(ref["table_sha256"]).decode().split("\n")
+    ref["mod_off"] = np.concatenate([[0], np.cumsum(batch["n_mod"])]).astype(np.int64)
+    return meta, batch, ref
+
+
+def table_digest(bits, cnt, sc, w, tot):
+    import hashlib
+    h = hashlib.sha256()
+    for a, dt in ((bits, np.uint64), (cnt, np.int32), (sc, np.float32), (w, np.float32), (tot, np.int32)):
+        h.update(np.ascontiguousarray(a, dt).tobytes())
+    return h.hexdigest()
+
+
+def sig_bits(sig):
+    bits = np.zeros(sig.shape[0], np.uint64)
+    for j in range(sig.shape[1]):
+        bits |= sig[:, j].astype(np.uint64) << np.uint64(j)
+    return bits

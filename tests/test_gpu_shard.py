@@ -1,0 +1,181 @@
+"""GPU: the range / asynchronous / multi-device entry points of the C ABI and the sharded CLI.
+
+A batch cut into PSM ranges (pa_score_range), scored asynchronously (pa_score_batch_async + pa_wait) or sharded
+over several scorers by `MultiScorer` (pa_shard_ranges: cuts on spectrum boundaries) must give, bit for bit, the
+result of one pa_score_batch call over the whole batch.  With one GPU the scorers share it (devices [0, 0]); with
+more, every visible GPU takes a range.
+"""
+import numpy as np
+import pytest
+
+import _golden
+import _msfiles
+from pyascore_b200 import synth
+from test_gpu_cli import _argv, _compare
+from test_parsing import load_config1
+
+pytestmark = pytest.mark.gpu
+
+WORKLOADS = [("acetyl_k", 2999), ("hires_phospho_nl", 2500), ("lowres_phospho", 4000)]
+
+
+def _scorer(workload, cls=None, **kw):
+    from pyascore_b200 import Scorer
+    w = synth.WORKLOADS[workload]
+    s = (cls or Scorer)(**w["scorer"], **kw)
+    for g, m in w["neutral_losses"]:
+        s.add_neutral_loss(g, m)
+    return s
+
+
+def _same(a, b):
+    return all(np.asarray(a[k]).tobytes() == np.asarray(b[k]).tobytes() for k in a)
+
+
+def _devices():
+    import torch
+    n = torch.cuda.device_count()
+    return [[0, 0], [0, 0, 0]] + ([list(range(n))] if n > 1 else [])
+
+
+@pytest.mark.parametrize("workload,n", WORKLOADS)
+def test_ranges_equal_whole(workload, n):
+    batch = synth.make_batch(workload, n, seed=99, chunk_index=1)
+    s = _scorer(workload)
+    whole = s.score_batch(batch)
+    npsm = batch["n_mod"].size
+    out = {k: np.full_like(v, 0x55) for k, v in whole.items()}
+    cuts = [0, npsm // 7, npsm // 7, npsm // 2, npsm]              # an empty range in the middle; cuts may split a spectrum's hits
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s.score_batch(batch, out=out, psm_range=(a, b))
+        assert s.counters()["n_psm"] == b - a
+    assert _same(whole, out)
+    with pytest.raises(ValueError):
+        s.score_batch(batch, psm_range=(5, npsm + 1))
+    s.close()
+
+
+@pytest.mark.parametrize("workload,n", WORKLOADS)
+def test_multiscorer_sharded_equals_unsharded(workload, n):
+    from pyascore_b200 import MultiScorer, pin_batch
+    batch = synth.make_batch(workload, n, seed=123, chunk_index=2)
+    s = _scorer(workload)
+    whole = s.score_batch(batch)
+    s.close()
+    for devices in _devices():
+        ms = _scorer(workload, MultiScorer, devices=devices)
+        got = ms.score_batch(pin_batch(batch))
+        assert _same(whole, got), devices
+        ranges = ms.last_ranges
+        assert ranges[0][0] == 0 and ranges[-1][1] == batch["n_mod"].size and len(ranges) == len(devices)
+        for (a0, a1), (b0, b1) in zip(ranges[:-1], ranges[1:]):
+            assert a1 == b0
+            if 0 < a1 < batch["n_mod"].size:
+                assert batch["psm_spec"][a1] != batch["psm_spec"][a1 - 1]      # a spectrum is binned by one GPU only
+        assert sum(c["n_psm"] for c in ms.counters()) == batch["n_mod"].size
+        ms.close()
+
+
+def test_async_and_wait():
+    import torch
+    batch = synth.make_batch("lowres_phospho", 3000, seed=5, chunk_index=0)
+    s = _scorer("lowres_phospho")
+    whole = s.score_batch(batch)
+    out = s.score_batch_async(batch)
+    with pytest.raises(ValueError):
+        s.score_batch(batch)                  # one call in flight per scorer
+    s.wait()
+    s.wait()                                  # nothing in flight: returns at once
+    assert _same(whole, out)
+    # device-resident inputs produced on the caller's stream: the call must order itself after them
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        dev = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda(non_blocking=True) for k, v in batch.items()}
+    out_d = s.score_batch_async(dev, stream=st)
+    s.wait()
+    assert all(out_d[k].cpu().numpy().tobytes() == np.asarray(whole[k]).tobytes() for k in whole)
+    s.close()
+
+
+def test_inconsistent_batches_are_refused():
+    """CSR arrays that do not describe a batch come back as PA_ERR_ARG (ValueError), on both input sides"""
+    import torch
+    base = synth.make_batch("acetyl_k", 300, seed=1)
+    s = _scorer("acetyl_k")
+    s.score_batch(dict(base))
+
+    def broken(which):
+        b = {k: v.copy() for k, v in base.items()}
+        if which == "spec_off":
+            b["spec_off"][5] = b["spec_off"][4] - 3
+        elif which == "pep_off":
+            b["pep_off"][10] = b["pep_off"][11] + 4
+        elif which == "aux_off":
+            b["aux_off"][-1] = -2
+        elif which == "mod_off":
+            mo = np.zeros(b["n_mod"].size + 1, np.int64)
+            np.cumsum(b["n_mod"], out=mo[1:])
+            mo[7:] += 1
+            b["mod_off"] = mo
+        elif which == "aux_null":
+            b["aux_pos"] = None
+        return b
+    for which in ("spec_off", "pep_off", "aux_off", "mod_off", "aux_null"):
+        with pytest.raises(ValueError):
+            s.score_batch(broken(which))
+        if which != "aux_null":
+            b = broken(which)
+            dev = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda() for k, v in b.items()}
+            with pytest.raises(ValueError):
+                s.score_batch(dev)
+    res = s.score_batch(dict(base))           # the scorer is still usable
+    assert np.all(res["psm_status"] == 0)
+    s.close()
+
+
+def test_long_peptide_with_neutral_losses_is_scored():
+    """fragment budget: counted from the peptide's own neutral-loss stack, not the scorer's worst case
+    (a long, high-charge peptide under 3 loss masses used to come back PA_PSM_TOO_MANY_FRAGMENTS)"""
+    from oracle.cscorer import OraclePyAscore
+    from pyascore_b200 import PyAscore
+    rng = np.random.default_rng(3)
+    pep = "AGLPEVAGLPEVAGLPEVAGLPEVAGLPEVAGLPEVAGLPEVAGLPEVAGLPEVAGLPEVAGLPSTK"      # 66 residues, losses only at the end
+    mz = np.sort(rng.uniform(150., 2000., 400)); inten = rng.lognormal(5., 1., 400)
+    kw = dict(bin_size=100., n_top=10, mod_group="STY", mod_mass=79.966331, mz_error=0.05, fragment_types="by")
+    a, O = PyAscore(**kw), OraclePyAscore(**kw)
+    for sc in (a, O):
+        for g, m in (("ST", 18.01528), ("st", 97.9769), ("K", 17.026549)):
+            sc.add_neutral_loss(g, m)
+    a.score(mz, inten, pep, 1, 4)
+    O.score(mz, inten, pep, 1, 4)
+    assert a.best_sequence == O.best_sequence
+    assert _golden.same_bits(np.float32(a.best_score), np.float32(O.best_score))
+    assert _golden.same_bits(a.ascores, O.ascores)
+
+
+@pytest.mark.parametrize("fmt", ["percolatorTXT", "mokapotTXT"])
+def test_config1_cli_bracket_tables(tmp_path, fmt):
+    """BASELINE config 1 with the identifications as a percolator / mokapot table: same TSV as the pepXML path
+    (the extractors themselves are pinned to the reference's code by tests/golden/idparse)"""
+    from pyascore_b200.__main__ import main
+    spectra, queries, expected = load_config1()
+    spec, ident, out = str(tmp_path / "s.mzML"), str(tmp_path / "i.txt"), str(tmp_path / "o.tsv")
+    _msfiles.write_mzml(spec, spectra, inten_bits=32)
+    (_msfiles.write_percolator_txt if fmt == "percolatorTXT" else _msfiles.write_mokapot_txt)(ident, queries)
+    for setting in ("default", "hit_depth2"):
+        main(_argv(expected[setting]["args"]) + ["--ident_file_type", fmt, spec, ident, out])
+        _compare(open(out).read(), expected[setting]["tsv"])
+
+
+def test_config1_cli_sharded(tmp_path):
+    """--devices: every chunk sharded over the listed GPUs, byte-identical TSV"""
+    import torch
+    from pyascore_b200.__main__ import main
+    spectra, queries, expected = load_config1()
+    spec, ident, out = str(tmp_path / "s.mzML"), str(tmp_path / "i.pep.xml"), str(tmp_path / "o.tsv")
+    _msfiles.write_mzml(spec, spectra, inten_bits=32)
+    _msfiles.write_pepxml(ident, queries)
+    devs = ",".join(str(d) for d in (range(torch.cuda.device_count()) if torch.cuda.device_count() > 1 else (0, 0)))
+    for setting in ("default", "hires_nl"):
+        main(_argv(expected[setting]["args"]) + ["--devices", devs, spec, ident, out])
+        _compare(open(out).read(), expected[setting]["tsv"])

@@ -51,3 +51,26 @@ def test_oracle_stress_one():
     assert _golden.same_bits(w, ref["iso_weighted"][:b])             # full std::sort order of 15504 isoforms
     assert _golden.same_bits(cnt, ref["iso_counts"][:b])
     assert _golden.same_bits(O.ascores, ref["ascores"][:5])
+
+
+@pytest.mark.parametrize("name", _golden.big_names())
+def test_oracle_matches_big_golden(name):
+    """stress PSMs (15504 isoforms) and all-tie inputs up to 15504 isoforms in "by" and "yb" order: results and the
+    SHA-256 of the whole pep_scores table in the reference's listing order (tests/golden/make_golden_big.py)"""
+    meta, batch, ref = _golden.load_big(name)
+    O = OraclePyAscore(**meta["scorer"])
+    for g, m in meta["neutral_losses"]:
+        O.add_neutral_loss(g, m)
+    n = batch["n_mod"].size
+    for i in range(n if not name.startswith("stress") else 10):       # ~0.4 s per stress PSM in the naive oracle
+        O.score(*synth.psm_view(batch, i))
+        sig, cnt, sc, w, tot = O.pep_score_tables()
+        assert w.size == int(ref["n_iso"][i])
+        assert O.best_sequence == ref["best_sequence"][i]
+        assert _golden.same_bits(np.float32(O.best_score), np.float32(ref["best_score"][i]))
+        assert _golden.table_digest(_golden.sig_bits(sig), cnt, sc, w, tot) == ref["table_sha256"][i]
+        k = int(batch["n_mod"][i])
+        mo = int(ref["mod_off"][i])
+        assert _golden.same_bits(O.ascores, ref["ascores"][mo:mo + k])
+        for j, alt in enumerate(O.alt_sites):
+            assert _golden.same_bits(alt, _golden.ref_alt(ref, i, j))

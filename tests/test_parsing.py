@@ -12,6 +12,7 @@ import _msfiles
 from pyascore_b200.parsing import (IdentificationParser, MassCorrector, PsmPacker, SpectraParser, iter_batches,
                                    process_mods, write_tsv)
 from pyascore_b200.parsing._xml import STD_AA_MASS
+from pyascore_b200.parsing.id_parsers import COMMON_MODS
 from pyascore_b200.parsing.packer import fragment_charge
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -296,3 +297,30 @@ def test_power_set_sum():
             m = L.orc_power_set_sum(t.ctypes.data, n, depth, ref.ctypes.data, 256)
             got = np.array(drain(PyPowerSetSum(t, depth)), np.float32)
             assert got.tobytes() == ref[:m].tobytes(), (n, depth, got, ref[:m])
+
+
+# ---- percolator / mokapot tables pinned to the reference's own extractors ------------------------
+def _idparse_fixtures():
+    import glob
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "idparse", "*.json")))
+
+
+@pytest.mark.parametrize("path", _idparse_fixtures(), ids=lambda p: os.path.basename(p)[:-5])
+def test_bracket_tables_match_reference_extractors(tmp_path, path):
+    """records of the REFERENCE's PercolatorTXTExtractor / MokapotTXTExtractor + IdentificationParser run on these
+    tables (tests/golden/make_idparse.py) -- same records, same order, same dtypes from ours"""
+    import json
+    import warnings
+    fx = json.load(open(path))
+    f = tmp_path / "t.txt"
+    f.write_text(fx["table"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = IdentificationParser(str(f), fx["format"], MassCorrector(mod_mass_dict=dict(COMMON_MODS)), **fx["kwargs"]).to_list()
+    assert len(got) == len(fx["records"])
+    for g, w in zip(got, fx["records"]):
+        assert g["scan"] == w["scan"] and g["peptide"] == w["peptide"]
+        assert g["charge_state"] == w["charge_state"]
+        assert g["score"] == w["score"]
+        assert [int(x) for x in g["mod_positions"]] == w["mod_positions"]
+        assert [float(x) for x in g["mod_masses"]] == w["mod_masses"]          # exact: same float arithmetic
