@@ -810,6 +810,7 @@ struct PaSelArgs {
     int32_t* psm_status_out;
     // scratch
     unsigned long long* g_sort;  // per isoform (iso_off), for std::sort emulation beyond PA_SORTCAP
+    uint32_t* g_lr;              // partition stop lists of the warp replay: iso_off[p] + 2 p, n/2 + 1 entries per side
     int64_t mod_lo;              // absolute index of the chunk's first mod entry
     uint32_t* best_idx;          // [n_psm] best isoform (lexicographic rank), 0xffffffff = none
     int32_t* mod_psm;            // [entries] chunk-relative PSM of each mod entry, -1 = no Ascore to compute
@@ -960,6 +961,86 @@ __device__ uint32_t pa_gcc_sort_front(unsigned long long* a, long n) {
     long bi = 0;
     for (long i = 1; i < last; i++) if (SRT_CMP(a[i], a[bi])) bi = i;
     return (uint32_t)(a[bi] & 0xffffffffull);
+}
+
+// The same replay run by a whole WARP, for isoform sets too large for one lane's shared-memory arena (`a` lives in
+// global memory; a single lane walking it pays an L2 round trip per element: 5.8 ms on the 15 504-isoform stress
+// config).  One partition of std::__unguarded_partition is a function of the ORIGINAL arrangement: with
+//   L_0 < L_1 < ...  the positions in [1, last) whose element does not beat the pivot   (where `first` stops),
+//   R_0 > R_1 > ...  the positions the pivot does not beat, from the right               (where `last` stops),
+// the sequential loop swaps the pairs (L_t, R_t) while L_t < R_t -- the elements between two stops are never
+// touched, and a position a swap has filled stops the opposite cursor exactly where the next original stop or the
+// swapped position comes first -- and returns cut = min(L_m, R_{m-1}) for the first m with L_m >= R_m.  Both stop
+// lists are stream compactions (ballot + popc), the swaps are independent, so a partition costs two coalesced
+// passes.  Only the first n/2 + 1 stops of each side can pair; `lst` holds 2 * (n/2 + 1) indices.
+__device__ uint32_t pa_gcc_sort_front_warp(unsigned long long* a, long n, uint32_t* lst) {
+    const int lane = threadIdx.x & 31;
+    if (n < 1) return 0xffffffffu;
+    long lg = 0;
+    for (long t = n; t > 1; t >>= 1) lg++;
+    long last = n, depth = 2 * lg;
+    const long cap = n / 2 + 1;
+    uint32_t* Ls = lst;
+    uint32_t* Rs = lst + cap;
+    const unsigned below = (1u << lane) - 1u;
+    while (last > 16) {
+        if (depth == 0) {                    // introsort's heap-sort fallback: sequential, as rare as in the reference
+            unsigned long long r = 0;
+            if (lane == 0) { srt_heap_sort(a, last); r = a[0]; }
+            r = __shfl_sync(PA_FULL, r, 0);
+            return (uint32_t)(r & 0xffffffffull);
+        }
+        --depth;
+        if (lane == 0) {                     // median of a[1], a[mid], a[last-1] to the front (std::__move_median_to_first)
+            const long mid = last / 2;
+            const long x = 1, y = mid, z = last - 1;
+            long pick;
+            if (SRT_CMP(a[x], a[y])) { if (SRT_CMP(a[y], a[z])) pick = y; else if (SRT_CMP(a[x], a[z])) pick = z; else pick = x; }
+            else if (SRT_CMP(a[x], a[z])) pick = x; else if (SRT_CMP(a[y], a[z])) pick = z; else pick = y;
+            const unsigned long long t = a[0]; a[0] = a[pick]; a[pick] = t;
+        }
+        __syncwarp();
+        const unsigned long long pv = a[0];
+        long nL = 0, nR = 0;
+        for (long base = 1; base < last; base += 32) {
+            const long i = base + lane, j = last - base - lane;          // i ascends from 1, j descends from last - 1
+            const bool okL = i < last && !SRT_CMP(a[i], pv);
+            const bool okR = j >= 1 && !SRT_CMP(pv, a[j]);
+            const unsigned bl = __ballot_sync(PA_FULL, okL), br = __ballot_sync(PA_FULL, okR);
+            const long pl = nL + __popc(bl & below), pr = nR + __popc(br & below);
+            if (okL && pl < cap) Ls[pl] = (uint32_t)i;
+            if (okR && pr < cap) Rs[pr] = (uint32_t)j;
+            nL += __popc(bl); nR += __popc(br);
+        }
+        __syncwarp();
+        long lim = nL < nR ? nL : nR;
+        lim = lim < cap ? lim : cap;
+        // proper pairs: a prefix of t (L ascends, R descends)
+        long m = 0;
+        for (long t0 = 0; t0 < lim; t0 += 32) {
+            const long t = t0 + lane;
+            const unsigned ok = __ballot_sync(PA_FULL, t < lim && Ls[t] < Rs[t]);
+            m += __popc(ok);
+            if (ok != PA_FULL) break;
+        }
+        for (long t = lane; t < m; t += 32) {
+            const uint32_t l = Ls[t], r = Rs[t];
+            const unsigned long long tmp = a[l]; a[l] = a[r]; a[r] = tmp;
+        }
+        long cut = last;                     // (a stop always exists: the median-of-three leaves one on either side)
+        if (m < nL && m < cap) cut = Ls[m];
+        if (m > 0 && (long)Rs[m - 1] < cut) cut = Rs[m - 1];
+        __syncwarp();
+        last = cut;
+    }
+    // the closing insertion sort is stable on the left-most segment: its first maximal element comes to the front
+    unsigned long long e = lane < last ? a[lane] : 0ull;
+    float w = lane < last ? srt_w(e) : -INFINITY;
+    float wm = w;
+    for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(PA_FULL, wm, o); wm = t > wm ? t : wm; }
+    const unsigned is = __ballot_sync(PA_FULL, lane < last && w == wm);
+    e = __shfl_sync(PA_FULL, e, __ffs(is) - 1);
+    return (uint32_t)(e & 0xffffffffull);
 }
 
 // --- site-determining ions of isoforms A (slot 0) and B (slot 1) for one ion type ------------
@@ -1364,8 +1445,10 @@ __global__ void __launch_bounds__(256) k_select(PaCfg cfg, PaBatchDev b, PaSelAr
                     arr[q] = ((unsigned long long)(uint32_t)__float_as_int(a.iso.w[ib + id]) << 32) | id;
                 }
                 __syncwarp();
-                if (lane == 0) best = pa_gcc_sort_front(arr, (long)I);
-                best = __shfl_sync(PA_FULL, best, 0);
+                if (I <= PA_SORTCAP) {       // shared-memory arena: one lane replays the partitions
+                    if (lane == 0) best = pa_gcc_sort_front(arr, (long)I);
+                    best = __shfl_sync(PA_FULL, best, 0);
+                } else best = pa_gcc_sort_front_warp(arr, (long)I, a.g_lr + ib + 2 * p);
                 __syncwarp();
             }
         }
@@ -1951,6 +2034,8 @@ __global__ void __launch_bounds__(128, (NQ <= 1 ? PA_ASC_MINBLOCKS : (NQ <= 2 ? 
     for (int c = 0; c < CLS; c++) first += a.work_count[c];
     asc_entry<NQ>(cfg, b, a, a.work_sorted[first + w]);
 }
+
+#include "pa_ascore.cuh"
 
 // K3c: generic (warp-cooperative, list-materialising) Ascore for the entries k_ascore queued.
 __global__ void __launch_bounds__(256) k_ascore_generic(PaCfg cfg, PaBatchDev b, PaAscArgs a, float* g_lists,

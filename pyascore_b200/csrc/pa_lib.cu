@@ -68,7 +68,7 @@ struct Slot {                // per-stream working set
     // plan
     DevBuf psm_S, psm_status, psm_I, psm_units, iso_off, unit_off, unit_psm, totals, cub_tmp;
     // K2/K3
-    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lists, lookups, sched, best_idx, mod_psm, tie, generic_list, generic_count, work_key, work_key2, work_val, work_sorted, rest_list;
+    DevBuf iso_lo, iso_hi, iso_n, iso_w, g_sort, g_lr, g_lists, lookups, sched, best_idx, mod_psm, tie, generic_list, generic_count, work_key, work_key2, work_val, work_sorted, rest_list, item_cnt, item_off, gen_flag, asc_cursor;
     // staged outputs
     DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
     PlanTotals* h_totals = nullptr;      // pinned
@@ -78,7 +78,7 @@ struct Slot {                // per-stream working set
         DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rpk, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lr, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &item_cnt, &item_off, &gen_flag, &asc_cursor, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_totals) cudaFreeHost(h_totals);
@@ -128,6 +128,7 @@ struct pa_scorer {
     size_t ev_used = 0;
     int attr_set = 0;
     bool binner_only = false;
+    int asc_form = 3;                      // PA_ASC_FORM=1|2|3: form of K3b (A/B runs); 3 = pairs from a global cursor
     // pa_score_batch_async: one orchestration thread per call in flight (at most one per scorer)
     std::thread worker;
     bool busy = false;
@@ -485,6 +486,7 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
     s = new pa_scorer();
     s->device = device;
     s->binner_only = binner_only;
+    { const char* e = getenv("PA_ASC_FORM"); if (e && e[0] >= '1' && e[0] <= '3') s->asc_form = e[0] - '0'; }
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     s->mod_group = mod_group; s->frag_types = fragment_types;
     s->bin_size = bin_size; s->mod_mass = mod_mass; s->err = mz_error; s->n_top = n_top;
@@ -526,6 +528,12 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
         }
         CK(cudaFuncSetAttribute(k_ascore_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_ascore<PA_MAXSTREAM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm)));
+        CK(cudaFuncSetAttribute(k_ascore_pairs<PA_MAXSTREAM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm)));
+        CK(cudaFuncSetAttribute(k_ascore_items<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<1, false>)));
+        CK(cudaFuncSetAttribute(k_ascore_items<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<2, false>)));
+        CK(cudaFuncSetAttribute(k_ascore_items<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<4, false>)));
+        CK(cudaFuncSetAttribute(k_ascore_items<PA_MAXSTREAM, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<PA_MAXSTREAM, false>)));
+        CK(cudaFuncSetAttribute(k_ascore_items<PA_MAXSTREAM, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<PA_MAXSTREAM, true>)));
         CK(cudaFuncSetAttribute(k_bin_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_tail_table, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(k_ambiguity, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -816,6 +824,7 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     CK(sl.iso_n.ensure((size_t)std::max<int64_t>(total_iso, 1) * 4));
     CK(sl.iso_w.ensure((size_t)std::max<int64_t>(total_iso, 1) * 4));
     CK(sl.g_sort.ensure((size_t)std::max<int64_t>(total_iso, 1) * 8));
+    CK(sl.g_lr.ensure((size_t)(std::max<int64_t>(total_iso, 1) + 2 * np + 2) * 4));
     CK(sl.unit_psm.ensure((size_t)std::max(n_units, 1) * 4));
     PaIso iso;
     iso.lo = sl.iso_lo.as<unsigned long long>(); iso.hi = sl.iso_hi.as<unsigned long long>();
@@ -891,7 +900,7 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
         sa.n_sites = cs.o_nsites ? cs.o_nsites + r.p0 : nullptr;
         sa.ascores = cs.o_asc; sa.alt_sites = cs.o_alt;            // indexed with absolute mod_off
         sa.psm_status_out = cs.o_status ? cs.o_status + r.p0 : nullptr;
-        sa.g_sort = sl.g_sort.as<unsigned long long>();
+        sa.g_sort = sl.g_sort.as<unsigned long long>(); sa.g_lr = sl.g_lr.as<uint32_t>();
         sa.mod_lo = cs.mod_lo; sa.best_idx = sl.best_idx.as<uint32_t>(); sa.mod_psm = sl.mod_psm.as<int32_t>();
         sa.tie = sl.tie.as<unsigned long long>();
         sa.work_key = sl.work_key.as<uint16_t>(); sa.work_val = sl.work_val.as<int32_t>();
@@ -933,13 +942,52 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
                                            sl.work_val.as<int32_t>(), sl.work_sorted.as<int32_t>(), (int)nm, 0, PA_WORK_BITS, st));
         s->ctr.kernel_launches += 3;
         const unsigned ab = (unsigned)((nm + 127) / 128);
-        if (!s->cfg.has_nl) {
-            k_ascore<1, 0><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
-            k_ascore<2, 1><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
-            k_ascore<4, 2><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
-            s->ctr.kernel_launches += 3;
+        if (s->asc_form == 3) {
+            // pairs (entry, tied competitor) numbered by a scan over the sorted entry list, handed out from a cursor
+            CK(sl.item_cnt.ensure((size_t)(nm + 1) * 4)); CK(sl.item_off.ensure((size_t)(nm + 1) * 4));
+            CK(sl.gen_flag.ensure((size_t)nm * 4));
+            CK(sl.asc_cursor.ensure(32));
+            CK(cudaMemsetAsync(sl.gen_flag.p, 0, (size_t)nm * 4, st));
+            CK(cudaMemsetAsync(sl.asc_cursor.p, 0, 32, st));
+            PaAscItemArgs ia;
+            ia.item_cnt = sl.item_cnt.as<int32_t>(); ia.item_off = sl.item_off.as<int32_t>();
+            ia.cursor = sl.asc_cursor.as<unsigned long long>(); ia.gen_flag = sl.gen_flag.as<int>();
+            k_asc_item_count<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(aa, ia);
+            size_t ts = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, ts, ia.item_cnt, sl.item_off.as<int32_t>(), (int)(nm + 1), st));
+            CK(sl.cub_tmp.ensure(ts + 256));
+            ts = sl.cub_tmp.cap;
+            CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, ts, ia.item_cnt, sl.item_off.as<int32_t>(), (int)(nm + 1), st));
+            s->ctr.kernel_launches += 2;
+#define PA_PAIRS_LAUNCH(NQ, CLS, SMEM) { \
+                const int blocks = (int)std::min<int64_t>(ab, (int64_t)s->sm_count * resident_blocks(k_ascore_pairs<NQ, CLS>, 128, SMEM)); \
+                k_ascore_pairs<NQ, CLS><<<blocks, 128, SMEM, st>>>(s->cfg, cs.b, aa, ia); }
+            if (!s->cfg.has_nl) {
+                PA_PAIRS_LAUNCH(1, 0, 0) PA_PAIRS_LAUNCH(2, 1, 0) PA_PAIRS_LAUNCH(4, 2, 0)
+                s->ctr.kernel_launches += 3;
+            }
+            PA_PAIRS_LAUNCH(PA_MAXSTREAM, 3, sizeof(AscSm))
+#undef PA_PAIRS_LAUNCH
+        } else if (s->asc_form == 1) {
+            if (!s->cfg.has_nl) {
+                k_ascore<1, 0><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
+                k_ascore<2, 1><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
+                k_ascore<4, 2><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
+                s->ctr.kernel_launches += 3;
+            }
+            k_ascore<PA_MAXSTREAM, 3><<<ab, ASC_BLOCK, sizeof(AscSm), st>>>(s->cfg, cs.b, aa);
+        } else {
+            // one warp per 32 entries of the work-sorted list (longest merges first: the block scheduler hands
+            // them out in that order); the entry count of a class is only known on the device
+            if (!s->cfg.has_nl) {
+                k_ascore_items<1, 0, false><<<ab, ASC_BLOCK, sizeof(AscSm2<1, false>), st>>>(s->cfg, cs.b, aa);
+                k_ascore_items<2, 1, false><<<ab, ASC_BLOCK, sizeof(AscSm2<2, false>), st>>>(s->cfg, cs.b, aa);
+                k_ascore_items<4, 2, false><<<ab, ASC_BLOCK, sizeof(AscSm2<4, false>), st>>>(s->cfg, cs.b, aa);
+                k_ascore_items<PA_MAXSTREAM, 3, false><<<ab, ASC_BLOCK, sizeof(AscSm2<PA_MAXSTREAM, false>), st>>>(s->cfg, cs.b, aa);
+                s->ctr.kernel_launches += 3;
+            } else
+                k_ascore_items<PA_MAXSTREAM, 3, true><<<ab, ASC_BLOCK, sizeof(AscSm2<PA_MAXSTREAM, true>), st>>>(s->cfg, cs.b, aa);
         }
-        k_ascore<PA_MAXSTREAM, 3><<<ab, ASC_BLOCK, sizeof(AscSm), st>>>(s->cfg, cs.b, aa);
         CK(cudaGetLastError());
         const int wpb = 8;
         int blocks = s->sm_count * 2;

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for SO in build/variants/libpa_*.so; do
   V=$(basename $SO .so | sed s/libpa_//)
   for W in ${@:-lowres_phospho}; do
-    PYASCORE_B200_LIB=$PWD/$SO python bench.py --workload $W --steps 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_${V}_$W.json 2> gpurun_out/${TAG}_${V}_$W.err
+    PYASCORE_B200_LIB=$PWD/$SO python bench.py --workload $W --steps 3 --no-cpu-baseline --no-e2e --no-configs > gpurun_out/${TAG}_${V}_$W.json 2> gpurun_out/${TAG}_${V}_$W.err
     python - <<PY
 import json
 try:
