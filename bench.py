@@ -484,10 +484,15 @@ def main():
             ms += ctr["ms_total"]
         return ms, time.perf_counter() - t, ctr
 
-    def h2d_gbs(nbytes=1 << 30, reps=4, together=False):
+    def h2d_gbs(nbytes=1 << 30, reps=4, together=False, wc=False):
         """pinned-host -> device copy rate of this rank's GPU; `together`: every rank copies at the same time
-        (after a barrier), which is what the end-to-end leg of an N-rank run is up against"""
-        src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        (after a barrier), which is what the end-to-end leg of an N-rank run is up against; `wc`: from
+        write-combined pinned pages"""
+        if wc:
+            src = torch.from_numpy(pb.pinned_empty(nbytes, np.uint8, pb.PINNED_WRITE_COMBINED))
+            src[:4096].zero_()
+        else:
+            src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
         best = 0.0
@@ -499,14 +504,21 @@ def main():
             best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
         return best
 
-    pcie_gbs = pcie_together = None
+    pcie_gbs = pcie_together = pcie_wc = pcie_together_wc = None
     if not args.no_e2e:
         pcie_gbs = h2d_gbs()
+        try:
+            pcie_wc = h2d_gbs(wc=True)
+        except Exception:
+            pcie_wc = None
         if world > 1:
-            mine = torch.tensor([h2d_gbs(together=True)], dtype=torch.float64, device="cuda")
-            allr = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allr, mine)
-            pcie_together = [float(x.item()) for x in allr]
+            def gather(v):
+                mine = torch.tensor([v], dtype=torch.float64, device="cuda")
+                allr = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allr, mine)
+                return [float(x.item()) for x in allr]
+            pcie_together = gather(h2d_gbs(together=True))
+            pcie_together_wc = gather(h2d_gbs(together=True, wc=True))
     sampler = ClockSampler(local)
     # ---- value: inputs resident in HBM ----
     run_steps(dev, out_dev, args.warmup)
@@ -522,6 +534,33 @@ def main():
     ms_e2e *= args.steps / e2e_steps
     wall_e2e *= args.steps / e2e_steps
     barrier()
+    # ---- e2e with float32 intensities (pa_batch.inten32): the form the parsing layer hands over when the file stores
+    # 32-bit intensity arrays.  The workload's intensities rounded to float32; checked bit for bit against the same
+    # values scored as float64.
+    f32_leg = None
+    if not args.no_e2e and world == 1:
+        try:
+            i32 = batch["inten"].astype(np.float32)
+            host32 = {k: v for k, v in host.items() if k != "inten"}
+            host32["inten32"] = pb.pinned_empty(i32.size, np.float32)
+            host32["inten32"][...] = i32
+            out32 = out_host_for(n_psm, mod_total)
+            run_steps(host32, out32, 1)
+            ms32, wall32, ctr32 = run_steps(host32, out32, args.steps)
+            host64r = dict(host)
+            host64r["inten"] = pb.pinned_empty(i32.size, np.float64)
+            host64r["inten"][...] = i32
+            out64r = out_host_for(n_psm, mod_total)
+            run_steps(host64r, out64r, 1)
+            f32_leg = {"value": n_psm * args.steps / wall32, "unit": "PSM/s", "ms_per_step": wall32 / args.steps * 1e3,
+                       "h2d_bytes_per_step": int(ctr32["bytes_h2d"]),
+                       "h2d_achieved_gbs": ctr32["bytes_h2d"] / (wall32 / args.steps) / 1e9,
+                       "equals_float64_of_same_values_bit_for_bit": all(out32[k].tobytes() == out64r[k].tobytes() for k in out32),
+                       "note": "same workload with the intensities rounded to float32 and passed as pa_batch.inten32 "
+                               "(12 instead of 16 bytes per peak over the host link)"}
+            del host32, host64r, out32, out64r
+        except Exception as e:          # noqa: BLE001
+            f32_leg = {"error": repr(e)}
     clocks = sampler.stop()
 
     # parity guard: both paths must agree bit for bit, and every PSM must have been scored
@@ -558,10 +597,12 @@ def main():
                     "ms_per_step_cuda_events": ms_e2e_max / args.steps,
                     "h2d_achieved_gbs": h2d_ach, "h2d_copy_peak_gbs": pcie_gbs,
                     "h2d_concurrent_peak_gbs": pcie_together,
+                    "h2d_copy_peak_write_combined_gbs": pcie_wc, "h2d_concurrent_peak_write_combined_gbs": pcie_together_wc,
                     "h2d_frac_of_ceiling": (h2d_ach / ceiling) if ceiling else None,
                     "note": "bound by the host->device link: h2d_achieved_gbs (rank 0's bytes / the slowest rank's time) vs a "
                             "plain pinned 1 GiB copy alone (h2d_copy_peak_gbs) and with every rank copying at once "
                             "(h2d_concurrent_peak_gbs, per rank; the ceiling is the slowest)"},
+            "e2e_f32_intensity": f32_leg,
             "gpu_launches": int(ctr_dev["kernel_launches"]) * args.steps,
             "roofline": roofline_of(args.workload, batch, mod_total, ctr_dev, peak, peak_src, clocks, sm_count),
             "kernel_ms_per_step": kern, "wall_ms_per_step": wall_dev_ms / args.steps,
@@ -648,11 +689,6 @@ def run_config(name, batch, n_dev, args, peak, peak_src, clocks, sm_count, torch
     pb.add_mod_off(batch)
     n = int(batch["n_mod"].size)
     mods = int(batch["mod_off"][-1])
-    policy = set_interleave(True) if n_dev > 1 else "single GPU"
-    host = pb.pin_batch(batch)
-    out_host = out_host_for(n, mods)
-    if n_dev > 1:
-        set_interleave(False)
     ms = MultiScorer(devices=list(range(n_dev)), **w["scorer"])
     for g, m in w["neutral_losses"]:
         ms.add_neutral_loss(g, m)
@@ -661,16 +697,42 @@ def run_config(name, batch, n_dev, args, peak, peak_src, clocks, sm_count, torch
         for d in range(n_dev):
             torch.cuda.synchronize(d)
 
-    # ---- end to end through MultiScorer.score_batch (cut + N concurrent ranges) ----
-    for _ in range(warm):
-        ms.score_batch(host, out=out_host)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        ms.score_batch(host, out=out_host)
-    e2e_s = (time.perf_counter() - t0) / steps
-    ctrs = ms.counters()
-    ranges = ms.last_ranges
+    out_host = out_host_for(n, mods)
+
+    def e2e_with(placement):
+        """end to end through MultiScorer.score_batch (cut + N concurrent ranges) with the batch pinned as `placement`
+        says: "default" (pages where this process runs), "interleaved" (round robin over the memory nodes: every GPU
+        reads half of its bytes from its own socket), "+wc" (m/z and intensities in write-combined pages)"""
+        note = "single GPU"
+        if n_dev > 1 and placement.startswith("interleaved"):
+            note = set_interleave(True)
+        host = pb.pin_batch(batch, flags=pb.PINNED_PORTABLE,
+                            peak_flags=(pb.PINNED_PORTABLE | pb.PINNED_WRITE_COMBINED) if placement.endswith("+wc") else None)
+        if n_dev > 1 and placement.startswith("interleaved"):
+            set_interleave(False)
+        for _ in range(warm):
+            ms.score_batch(host, out=out_host)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ms.score_batch(host, out=out_host)
+        dt = (time.perf_counter() - t0) / steps
+        return dt, note, ms.counters(), ms.last_ranges
+
+    placements = ["default"] if n_dev == 1 else ["default", "interleaved", "interleaved+wc"]
+    tried = {}
+    best = None
+    for pl in placements:
+        try:
+            r = e2e_with(pl)
+        except Exception as e:          # noqa: BLE001 -- a placement the box refuses is reported, not fatal
+            tried[pl] = {"error": repr(e)}
+            continue
+        tried[pl] = {"ms_per_step": r[0] * 1e3, "psm_per_s": n / r[0], "pages": r[1]}
+        if best is None or r[0] < best[1][0]:
+            best = (pl, r)
+    policy = best[0]
+    e2e_s, _, ctrs, ranges = best[1]
     h2d = sum(c["bytes_h2d"] for c in ctrs)
     # ---- every shard resident on its GPU ----
     shards = [shard.take_shard(batch, a, b) for a, b in ranges]
@@ -712,7 +774,7 @@ def run_config(name, batch, n_dev, args, peak, peak_src, clocks, sm_count, torch
         "e2e": {"value": n / e2e_s, "unit": "PSM/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(sum(c["bytes_d2h"] for c in ctrs)), "h2d_achieved_gbs": h2d / e2e_s / 1e9,
                 "timing": "wall clock around MultiScorer.score_batch (cut + every range), one process, pinned host arrays",
-                "pinned_pages": policy},
+                "pinned_pages": policy, "placements_tried": tried},
         "shard_psms": [b - a for a, b in ranges],
         "shard_ms_cuda_events": [c["ms_total"] for c in ctrs],
         "kernel_ms_per_step_gpu0": kernel_ms(ctr0),

@@ -91,6 +91,10 @@ typedef struct {
     const uint32_t* aux_pos;  /* aux_mod_pos: 0 = N-term, else 1-based residue */
     const float* aux_mass;    /* aux_mod_mass */
     const int64_t* mod_off;   /* [n_psm+1] exclusive prefix sum of n_mod: layout of ascores/alt_sites */
+    const float* inten32;     /* optional: the intensities as float32 (then `inten` may be NULL).  For callers that hold
+                               * them in that precision anyway -- mzML files store 32-bit intensity arrays -- it saves a
+                               * quarter of the bytes the host link carries.  (double)float is exact and monotone, so the
+                               * ranks are those the reference computes on the same values handed to it as float64 */
 } pa_batch;
 
 /* Outputs (caller-allocated; any pointer may be NULL to skip that result).
@@ -225,6 +229,13 @@ int pa_counters(const pa_scorer* s, pa_counters_t* out);
 /* Pinned host memory for CSR batches, so H2D/D2H copies run asynchronously. */
 void* pa_alloc_pinned(int64_t bytes);
 void pa_free_pinned(void* p);
+
+/* The same with placement flags.  PA_PINNED_PORTABLE: pinned for every CUDA context of the process (one batch read by
+ * the scorers of several GPUs).  PA_PINNED_WRITE_COMBINED: write-combined pages -- faster for the device to read on
+ * some hosts, very slow for the CPU to read back: only for arrays the host writes once (m/z, intensities). */
+#define PA_PINNED_WRITE_COMBINED 1u
+#define PA_PINNED_PORTABLE 2u
+void* pa_alloc_pinned_ex(int64_t bytes, uint32_t flags);
 
 /* Library/ABI version. */
 int pa_version(void);

@@ -67,15 +67,23 @@ def run(args, log=print):
                            hit_depth=args.hit_depth)
     rows = []
     saved = []
-    for scans, batch, res in score_stream(scorer, batches):
-        rows.extend(result_rows(scorer, scans, batch, res))
-        if args.match_save:
-            saved.append((scans, batch))
+    n_psm = 0
+    try:
+        for scans, batch, res in score_stream(scorer, batches):
+            rows.extend(result_rows(scorer, scans, batch, res))
+            n_psm += int(scans.size)
+            if args.match_save:
+                saved.append((scans, batch))
+    finally:
+        scorer.close()
     if args.match_save and saved:
         scans, batch = saved[-1]
-        np.savez("dump_batch.npz", scans=scans, **batch)
+        np.savez("dump_batch.npz", scans=scans, **{k: v for k, v in batch.items() if v is not None})
+    if len(rows) != n_psm:
+        # the reference would have written a row for these (or crashed on them): make the difference visible
+        log("{} -- {} of {} PSMs could not be scored (see the warnings) and have no row in the output".format(
+            _stamp(), n_psm - len(rows), n_psm))
     write_tsv(args.out_file, rows)
-    scorer.close()
     log("{} -- Ascore Completed".format(_stamp()))
     return rows
 

@@ -26,7 +26,7 @@ vp = C.c_void_p
 class PaBatch(C.Structure):
     _fields_ = [("n_spec", C.c_int64), ("spec_off", vp), ("mz", vp), ("inten", vp), ("n_psm", C.c_int64),
                 ("psm_spec", vp), ("pep_off", vp), ("pep", vp), ("n_mod", vp), ("max_charge", vp),
-                ("aux_off", vp), ("aux_pos", vp), ("aux_mass", vp), ("mod_off", vp)]
+                ("aux_off", vp), ("aux_pos", vp), ("aux_mass", vp), ("mod_off", vp), ("inten32", vp)]
 
 
 class PaResults(C.Structure):
@@ -46,7 +46,7 @@ EXPORTS = ["pa_create", "pa_add_neutral_loss", "pa_destroy", "pa_last_error", "p
            "pa_fetch_pep_scores", "pa_calculate_ambiguity", "pa_format_sequence", "pa_site_positions",
            "pa_bin_spectra", "pa_tail_table", "pa_counters", "pa_alloc_pinned", "pa_free_pinned", "pa_version",
            "pa_create_binner", "pa_bin_spectra_ex", "pa_fragment_table", "pa_site_determining_ions", "pa_log_math",
-           "pa_power_set_sums", "pa_score_range", "pa_score_batch_async", "pa_wait", "pa_shard_ranges", "pa_shard_ranges_for"]
+           "pa_power_set_sums", "pa_score_range", "pa_score_batch_async", "pa_wait", "pa_shard_ranges", "pa_shard_ranges_for", "pa_alloc_pinned_ex"]
 
 _lib = None
 
@@ -97,6 +97,8 @@ def load():
     L.pa_counters.argtypes = [vp, C.POINTER(PaCounters)]
     L.pa_alloc_pinned.restype = vp
     L.pa_alloc_pinned.argtypes = [C.c_int64]
+    L.pa_alloc_pinned_ex.restype = vp
+    L.pa_alloc_pinned_ex.argtypes = [C.c_int64, C.c_uint32]
     L.pa_free_pinned.restype = None
     L.pa_free_pinned.argtypes = [vp]
     L.pa_version.restype = C.c_int

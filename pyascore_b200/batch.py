@@ -13,10 +13,10 @@ import numpy as np
 from . import _lib
 
 _IN_KEYS = ("spec_off", "mz", "inten", "psm_spec", "pep_off", "pep", "n_mod", "max_charge",
-            "aux_off", "aux_pos", "aux_mass", "mod_off")
+            "aux_off", "aux_pos", "aux_mass", "mod_off", "inten32")
 _IN_DTYPES = dict(spec_off=np.int64, mz=np.float64, inten=np.float64, psm_spec=np.int32, pep_off=np.int32,
                   pep=np.uint8, n_mod=np.int32, max_charge=np.int32, aux_off=np.int32, aux_pos=np.uint32,
-                  aux_mass=np.float32, mod_off=np.int64)
+                  aux_mass=np.float32, mod_off=np.int64, inten32=np.float32)
 _OUT_DTYPES = dict(best_sig=np.uint64, best_score=np.float32, n_iso=np.int64, n_sites=np.int32,
                    ascores=np.float32, alt_sites=np.uint64, psm_status=np.int32)
 
@@ -27,9 +27,9 @@ _WANT_ALL = ("best_sig", "best_score", "n_iso", "n_sites", "ascores", "alt_sites
 class _Pinned:
     """numpy view over cudaMallocHost memory; freed when the last view dies."""
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, flags=0):
         self.L = _lib.load()
-        self.ptr = self.L.pa_alloc_pinned(max(int(nbytes), 1))
+        self.ptr = self.L.pa_alloc_pinned_ex(max(int(nbytes), 1), int(flags))
         if not self.ptr:
             raise MemoryError("pa_alloc_pinned(%d) failed" % nbytes)
         self.nbytes = int(nbytes)
@@ -40,20 +40,25 @@ class _Pinned:
             self.ptr = None
 
 
-def pinned_empty(shape, dtype):
+PINNED_WRITE_COMBINED, PINNED_PORTABLE = 1, 2
+
+
+def pinned_empty(shape, dtype, flags=0):
+    """numpy array over page-locked host memory (pa_alloc_pinned_ex; flags: PINNED_WRITE_COMBINED | PINNED_PORTABLE)"""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) if not np.isscalar(shape) else int(shape)
-    owner = _Pinned(n * dtype.itemsize)
+    owner = _Pinned(n * dtype.itemsize, flags)
     buf = (C.c_char * max(n * dtype.itemsize, 1)).from_address(owner.ptr)
     buf._pa_owner = owner            # the numpy view keeps `buf` (its base) and so the pinned block alive
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
 
-def pin_batch(batch):
-    """Copy a host batch into pinned memory (so H2D copies overlap compute)."""
+def pin_batch(batch, flags=0, peak_flags=None):
+    """Copy a host batch into pinned memory (so H2D copies overlap compute).  `peak_flags`: placement flags of the two
+    big arrays (m/z, intensities) when they differ from the rest, e.g. write-combined pages."""
     out = {}
     for k, v in batch.items():
-        a = pinned_empty(v.shape, v.dtype)
+        a = pinned_empty(v.shape, v.dtype, (peak_flags if peak_flags is not None and k in ("mz", "inten") else flags))
         a[...] = v
         out[k] = a
     return out

@@ -5,7 +5,8 @@
 //   K2  k_count_score    one warp per unit of <=1024 positional isoforms: fragments, matches, PepScore
 //   K3a k_select_thread  one thread per PSM: reference-order best isoform, tied competitors per site,
 //                        sort keys of the Ascore entries; k_select (one warp per PSM) for the PSMs it declines
-//   K3b k_ascore         one thread per (PSM, modified site): site-determining-ion merges -> Ascore
+//   K3b k_ascore_pairs   one thread per (PSM, modified site, tied competitor) pair, pairs handed out from a global
+//                        cursor in work-sorted order (pa_ascore.cuh): site-determining-ion merges -> Ascore
 //   K3c k_ascore_generic one warp per entry: list-materialising form for the shapes K3b declines
 // Nothing here is a dense contraction: no tensor cores.  The work is integer / float32 / a little
 // FP64 per fragment, bound by instruction issue and shared-memory latency.
@@ -66,7 +67,8 @@ __device__ __forceinline__ uint64_t pa_inten_key(double x) {
 struct PaBinArgs {
     const int64_t* spec_off;
     const double* mz;
-    const double* inten;
+    const double* inten;     // intensities as float64 (the reference's dtype), or
+    const float* inten32;    //   as float32 when the caller holds them in that precision (F32 instantiation)
     int64_t peak_base;       // spec_off values are relative to this
     int64_t n_spec;
     float2* rpk;             // retained peaks {(float)mz, rank as int bits}, m/z ascending, at the input offsets
@@ -99,6 +101,20 @@ struct PaBinArgs {
 #endif
 #define PA_BIN_SLOT_BYTES(cap) ((size_t)(cap) * 17 + PA_NBIN_SMEM * 4 + PA_NCELL)
 
+__device__ __forceinline__ uint32_t pa_inten_key32(float x) {
+    const uint32_t b = (uint32_t)__float_as_int(x);
+    return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ void pa_cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// F32: intensities arrive as float32 (4 instead of 8 bytes per peak over the host link and out of HBM).  A float is
+// its own ranking key and (double)float is exact and monotone, so the ranks are those the reference computes on the
+// same values handed to it as float64.
+template <bool F32>
 __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -129,7 +145,8 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             // in flight at once (the arrays are only 8-byte aligned at a CSR offset)
             for (int i = lane; i < P; i += 32) {
                 pa_cp_async8(&s_mz[i], a.mz + off + i);
-                pa_cp_async8(&s_key[i], a.inten + off + i);
+                if (F32) pa_cp_async4(&s_hi[i], a.inten32 + off + i);      // (lands where the ranking key of peak i will live)
+                else pa_cp_async8(&s_key[i], a.inten + off + i);
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -184,19 +201,21 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 if (v0) {
                     // (the second element of the pair may lie past the spectrum: still inside the slot)
                     const double2 m2 = *(const double2*)&s_mz[i0];
-                    const double2 t2 = *(const double2*)&s_key[i0];
+                    double2 t2 = make_double2(0., 0.);
+                    float2 t2f = make_float2(0.f, 0.f);
+                    if (F32) t2f = *(const float2*)&s_hi[i0]; else t2 = *(const double2*)&s_key[i0];
                     if (m2.x < mn || m2.x > mx) sorted = false;      // the ends must be the true extremes
                     bq0 = bin_of(m2.x);
                     mz0 = __double2float_rn(m2.x);
                     // ranking key: the intensity rounded to float.  The rounding is monotone, so two peaks
                     // with different keys are ordered as their doubles are, and peaks of one bin that
                     // share a key (ties, +-0, NaN) are caught below and ranked on the doubles instead
-                    k0 = __double2float_rn(t2.x);
+                    k0 = F32 ? t2f.x : __double2float_rn(t2.x);
                     if (v1) {
                         if (m2.y < mn || m2.y > mx) sorted = false;
                         bq1 = bin_of(m2.y);
                         mz1 = __double2float_rn(m2.y);
-                        k1 = __double2float_rn(t2.y);
+                        k1 = F32 ? t2f.y : __double2float_rn(t2.y);
                         if (bq1 < bq0 || mz1 < mz0) sorted = false;
                     }
                 }
@@ -229,10 +248,10 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             // global memory: only needed when two peaks of a bin share a float key, or n_top > 31);
             // an equal intensity wins only from an earlier index
             auto exact_rank = [&](int i, int b0, int b1) {
-                const uint64_t ki = pa_inten_key(a.inten[off + i]);
+                const uint64_t ki = F32 ? (uint64_t)pa_inten_key32(a.inten32[off + i]) : pa_inten_key(a.inten[off + i]);
                 int c = 0;
                 for (int j = b0; j < b1; j++) {
-                    const uint64_t kj = pa_inten_key(a.inten[off + j]);
+                    const uint64_t kj = F32 ? (uint64_t)pa_inten_key32(a.inten32[off + j]) : pa_inten_key(a.inten[off + j]);
                     c += (kj > ki) || (kj == ki && j < i);
                 }
                 return c;
@@ -389,11 +408,11 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             __syncwarp();
             for (int i = lane; i < P; i += 32) {
                 const int bq = a.g_bin[off + i];
-                const uint64_t ki = pa_inten_key(a.inten[off + i]);
+                const uint64_t ki = F32 ? (uint64_t)pa_inten_key32(a.inten32[off + i]) : pa_inten_key(a.inten[off + i]);
                 int cnt = 0;
                 for (int j = 0; j < P && cnt < n_top; j++) {
                     if (a.g_bin[off + j] != bq || j == i) continue;
-                    uint64_t kj = pa_inten_key(a.inten[off + j]);
+                    uint64_t kj = F32 ? (uint64_t)pa_inten_key32(a.inten32[off + j]) : pa_inten_key(a.inten[off + j]);
                     cnt += (kj > ki) || (kj == ki && j < i);
                 }
                 a.g_tmp[off + i] = (uint8_t)(cnt < n_top ? cnt : 255);
@@ -1920,97 +1939,6 @@ __device__ __forceinline__ int asc_site_pos(const PaCfg& cfg, const AscPep& q, i
     return 0;
 }
 
-template <int NQ>
-__device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b, const PaAscArgs& a, int64_t t) {
-    const int32_t p = a.mod_psm[t];
-    const int j = (int)(a.mod_lo + t - a.mod_off[p]);
-    const int S = a.psm_S[p], k = b.n_mod[p];
-    const int64_t ib = a.iso_off[p];
-    AscPep q;
-    const int po = b.pep_off[p];
-    q.pep = b.pep + po; q.L = b.pep_off[p + 1] - po; q.Z = b.max_charge[p];
-    q.a0 = 0; q.a1 = 0; q.aux_pos = b.aux_pos; q.aux_mass = b.aux_mass; q.aux_lo = 0; q.aux_hi = 0;
-    if (b.aux_off != nullptr) {
-        q.a0 = b.aux_off[p]; q.a1 = b.aux_off[p + 1];
-        for (int x = q.a0; x < q.a1; x++) {
-            const uint32_t pos = q.aux_pos[x];
-            const int idx = pos > 0 ? (int)pos - 1 : 0;
-            if (idx < 64) q.aux_lo |= 1ull << idx; else if (idx < 128) q.aux_hi |= 1ull << (idx - 64);
-        }
-    }
-    const int sp = b.psm_spec[p];
-    const int64_t off = b.spec_off[sp] - b.spec_base;
-    AscPeaks pk;
-    pk.pp = b.rpk + off; pk.R = b.rcount[sp];
-    pk.ctab = b.ctab + (size_t)sp * PA_NCELL;
-    { const float2 chead = b.chead[sp]; pk.cbase = chead.x; pk.cinv = chead.y; }
-
-    const uint32_t best = a.best_idx[p];
-    const uint64_t best_bits = pa_unrank(cfg.binom, S, k, best);
-    uint64_t rem = best_bits;
-    for (int jj = 0; jj < j; jj++) rem &= rem - 1;
-    const int site = __ffsll((long long)rem) - 1;
-    // residue mask of the best isoform and position of the site this entry is about
-    uint64_t alo = 0, ahi = 0;
-    int pos_site = 0;
-    {
-        int n = 0;
-        for (int i = 0; i < q.L && n < 64; i++) {
-            const int c = (int)q.pep[i] - 'A';
-            const bool is = ((cfg.mod_letters >> c) & 1u) || (cfg.allow_n && i == 0) || (cfg.allow_c && i == q.L - 1);
-            if (!is) continue;
-            if ((best_bits >> n) & 1ull) { if (i < 64) alo |= 1ull << i; else ahi |= 1ull << (i - 64); }
-            if (n == site) pos_site = i;
-            n++;
-        }
-    }
-    const unsigned long long loA = a.iso.lo[ib + best], hiA = a.iso.hi[ib + best];
-    const int nfA = (int)a.iso.nfrag[ib + best];
-    const float wA = a.iso.w[ib + best];
-
-    bool generic = (q.L < 2) || (NQ <= 4 && (cfg.has_nl || q.Z > NQ));
-    float asc = __int_as_float(0x7f800000);
-    for (uint64_t tt = a.tie[t]; tt && !generic; tt &= tt - 1) {
-        const int u = __ffsll((long long)tt) - 1;
-        const uint64_t cb = (best_bits & ~(1ull << site)) | (1ull << u);
-        const uint32_t ci = pa_rank(cfg.binom, S, k, cb);
-        const float wB = a.iso.w[ib + ci];
-        float amb = 0.f;
-        if (!((double)fabsf(__fsub_rn(wA, wB)) < 1e-6)) {
-            // depth with the largest score difference (cpp/Ascore.cpp:165-175), first strict maximum
-            const unsigned long long loB = a.iso.lo[ib + ci], hiB = a.iso.hi[ib + ci];
-            const int nfB = (int)a.iso.nfrag[ib + ci];
-            float max_diff = 0.f;
-            int depth = 0;
-            for (int d = 0; d < PA_N_TOP; d++) {
-                const float diff = __fsub_rn(__ldg(cfg.T + pa_tab_index(nfA, pa_cum_get(loA, hiA, d), d)),
-                                             __ldg(cfg.T + pa_tab_index(nfB, pa_cum_get(loB, hiB, d), d)));
-                if (diff > max_diff) { max_diff = diff; depth = d; }
-            }
-            // competitor mask = best mask with the mod moved from `site` to site u
-            uint64_t blo = alo, bhi = ahi;
-            { const int pos = pos_site; if (pos < 64) blo &= ~(1ull << pos); else bhi &= ~(1ull << (pos - 64)); }
-            { const int pos = asc_site_pos(cfg, q, u); if (pos < 64) blo |= 1ull << pos; else bhi |= 1ull << (pos - 64); }
-            int hitsA = 0, hitsB = 0, trialsA = 0, trialsB = 0;
-            for (int ti = 0; ti < cfg.n_types && !generic; ti++)
-                if (!asc_merge_type<NQ>(cfg, q, pk, cfg.types[ti], alo, ahi, blo, bhi, depth, hitsA, trialsA, hitsB, trialsB))
-                    generic = true;
-            if (!generic) {
-                const float sA = __ldg(cfg.T + pa_tab_index(trialsA, hitsA, depth));
-                const float sB = __ldg(cfg.T + pa_tab_index(trialsB, hitsB, depth));
-                amb = __fsub_rn(sA, sB);
-            }
-        }
-        asc = amb < asc ? amb : asc;
-    }
-    if (generic) {
-        const int slot = atomicAdd(a.generic_count, 1);
-        a.generic_list[slot] = (int32_t)t;
-        return;
-    }
-    if (a.ascores) a.ascores[a.mod_lo + t] = asc;
-}
-
 // One launch per stream class (0: one charge, 1: two, 2: up to four, 3: neutral losses or more
 // charges), so that each instantiation gets its own register budget and occupancy.
 #ifndef PA_ASC_MINBLOCKS
@@ -2025,16 +1953,6 @@ __device__ __forceinline__ void asc_entry(const PaCfg& cfg, const PaBatchDev& b,
 #ifndef PA_ASC12_MINBLOCKS
 #define PA_ASC12_MINBLOCKS 4
 #endif
-template <int NQ, int CLS>
-__global__ void __launch_bounds__(128, (NQ <= 1 ? PA_ASC_MINBLOCKS : (NQ <= 2 ? PA_ASC2_MINBLOCKS : (NQ <= 4 ? PA_ASC4_MINBLOCKS : PA_ASC12_MINBLOCKS)))) k_ascore(PaCfg cfg, PaBatchDev b, PaAscArgs a) {
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.work_count[CLS]) return;
-    int64_t first = 0;                       // classes are contiguous in the sorted list
-#pragma unroll
-    for (int c = 0; c < CLS; c++) first += a.work_count[c];
-    asc_entry<NQ>(cfg, b, a, a.work_sorted[first + w]);
-}
-
 #include "pa_ascore.cuh"
 
 // K3c: generic (warp-cooperative, list-materialising) Ascore for the entries k_ascore queued.

@@ -21,6 +21,7 @@
 
 #define PA_VERSION 200
 #define PA_CHUNK_PSM 131072
+#define PA_CHUNK_MIN 16384
 #define PA_CHUNK_PEAKS (96ll << 20)     // peaks per chunk (1.5 GB of float64 pairs)
 #define PA_TABLE_MIN 512
 
@@ -62,7 +63,7 @@ struct PlanTotals {          // device -> host after planning a chunk
 struct Slot {                // per-stream working set
     cudaStream_t st = nullptr;
     // staged inputs
-    DevBuf spec_off, mz, inten, psm_spec, pep_off, pep, n_mod, max_charge, aux_off, aux_pos, aux_mass, mod_off;
+    DevBuf spec_off, mz, inten, inten32, psm_spec, pep_off, pep, n_mod, max_charge, aux_off, aux_pos, aux_mass, mod_off;
     // K1
     DevBuf rpk, rmz, rrank, rcount, ctab, chead, g_bin, g_tmp;
     // plan
@@ -73,14 +74,22 @@ struct Slot {                // per-stream working set
     DevBuf o_sig, o_score, o_niso, o_nsites, o_asc, o_alt, o_status;
     PlanTotals* h_totals = nullptr;      // pinned
     unsigned long long* h_lookups = nullptr;
+    // small host batches (a single PyAscore.score call): every input array packed into one pinned block and copied
+    // with one transfer, every result array read back with one; the user's (pageable) arrays are touched by memcpy only
+    DevBuf d_pack, d_opack;
+    unsigned char* h_pack = nullptr; size_t h_pack_cap = 0;
+    unsigned char* h_opack = nullptr; size_t h_opack_cap = 0;
     cudaEvent_t ev_plan = nullptr;
     void release() {
-        DevBuf* all[] = {&spec_off, &mz, &inten, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
+        DevBuf* all[] = {&spec_off, &mz, &inten, &inten32, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rpk, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lr, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &item_cnt, &item_off, &gen_flag, &asc_cursor, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lr, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &item_cnt, &item_off, &gen_flag, &asc_cursor, &d_pack, &d_opack, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
+        if (h_pack) cudaFreeHost(h_pack);
+        if (h_opack) cudaFreeHost(h_opack);
+        h_pack = h_opack = nullptr; h_pack_cap = h_opack_cap = 0;
         if (h_totals) cudaFreeHost(h_totals);
         if (h_lookups) cudaFreeHost(h_lookups);
         if (ev_plan) cudaEventDestroy(ev_plan);
@@ -128,7 +137,6 @@ struct pa_scorer {
     size_t ev_used = 0;
     int attr_set = 0;
     bool binner_only = false;
-    int asc_form = 3;                      // PA_ASC_FORM=1|2|3: form of K3b (A/B runs); 3 = pairs from a global cursor
     // pa_score_batch_async: one orchestration thread per call in flight (at most one per scorer)
     std::thread worker;
     bool busy = false;
@@ -168,7 +176,7 @@ static void bin_launch_shape(int sm_count, int64_t max_peaks, int64_t n_spec, in
     for (int wpb = 8; wpb >= 1; wpb--) {
         const size_t smem = (size_t)wpb * PA_BIN_SLOT_BYTES(cap);
         if (smem > 200 * 1024) continue;
-        const int res = resident_blocks(k_bin_topn, wpb * 32, smem);
+        const int res = resident_blocks(k_bin_topn<false>, wpb * 32, smem);
         if (res * wpb > best_warps) { best_warps = res * wpb; best_wpb = wpb; best_res = res; }
     }
     *cap_out = cap; *wpb_out = best_wpb; *smem_out = (size_t)best_wpb * PA_BIN_SLOT_BYTES(cap);
@@ -459,6 +467,15 @@ extern "C" void* pa_alloc_pinned(int64_t bytes) {
     return p;
 }
 
+extern "C" void* pa_alloc_pinned_ex(int64_t bytes, uint32_t flags) {
+    void* p = nullptr;
+    unsigned f = cudaHostAllocDefault;
+    if (flags & PA_PINNED_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    if (flags & PA_PINNED_PORTABLE) f |= cudaHostAllocPortable;
+    if (cudaHostAlloc(&p, (size_t)std::max<int64_t>(bytes, 1), f) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
 extern "C" void pa_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 static int create_scorer(float bin_size, int n_top, const char* mod_group, float mod_mass, float mz_error,
@@ -486,7 +503,6 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
     s = new pa_scorer();
     s->device = device;
     s->binner_only = binner_only;
-    { const char* e = getenv("PA_ASC_FORM"); if (e && e[0] >= '1' && e[0] <= '3') s->asc_form = e[0] - '0'; }
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     s->mod_group = mod_group; s->frag_types = fragment_types;
     s->bin_size = bin_size; s->mod_mass = mod_mass; s->err = mz_error; s->n_top = n_top;
@@ -527,14 +543,9 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
             CK(cudaEventCreateWithFlags(&s->slot[i].ev_plan, cudaEventDisableTiming));
         }
         CK(cudaFuncSetAttribute(k_ascore_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(k_ascore<PA_MAXSTREAM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm)));
         CK(cudaFuncSetAttribute(k_ascore_pairs<PA_MAXSTREAM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm)));
-        CK(cudaFuncSetAttribute(k_ascore_items<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<1, false>)));
-        CK(cudaFuncSetAttribute(k_ascore_items<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<2, false>)));
-        CK(cudaFuncSetAttribute(k_ascore_items<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<4, false>)));
-        CK(cudaFuncSetAttribute(k_ascore_items<PA_MAXSTREAM, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<PA_MAXSTREAM, false>)));
-        CK(cudaFuncSetAttribute(k_ascore_items<PA_MAXSTREAM, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm2<PA_MAXSTREAM, true>)));
-        CK(cudaFuncSetAttribute(k_bin_topn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_bin_topn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_bin_topn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_tail_table, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(k_ambiguity, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         int r = refresh_config(s);
@@ -617,6 +628,32 @@ static cudaError_t copy_out(const DevBuf& buf, T* dst, bool on_dev, int64_t lo, 
     return cudaMemcpyAsync(dst + lo, buf.p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st);
 }
 
+#define PA_PACK_MAX (1 << 20)            // host batches up to this many input bytes travel as one packed block
+
+static cudaError_t ensure_pinned(unsigned char*& p, size_t& cap, size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 2 + 4096;
+    cudaError_t e = cudaMallocHost((void**)&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+
+struct PackIn {                          // cursor over the packed input block (host image + device address)
+    unsigned char* h; unsigned char* d; size_t used;
+    template <class T> const T* add(const T* src, int64_t lo, int64_t n) {      // -> device view indexed with ABSOLUTE indices
+        if (!src) return nullptr;
+        const size_t off = (used + 15) & ~(size_t)15;
+        if (n > 0) memcpy(h + off, src + lo, (size_t)n * sizeof(T));
+        used = off + (size_t)std::max<int64_t>(n, 0) * sizeof(T);
+        return (const T*)(d + off) - lo;
+    }
+};
+
+struct PackOut {                         // one packed result array: where it sits in the block, where it goes on the host
+    size_t off, bytes; void* dst;
+};
+
 // ---- chunk boundaries of a device-resident batch --------------------------------------------------
 // Chunks a device-resident batch is cut into (the two streams alternate).  Measured on config 2 (1 M PSMs):
 // 1 chunk 91.5 M PSM/s, 2 chunks 94.1 M, 4 chunks 84.0 M, 8 chunks 70.2 M -- the persistent kernels of two
@@ -688,6 +725,10 @@ struct ChunkState {              // what the back half of a chunk needs from the
     const int64_t* mod_off_abs = nullptr;
     cudaEvent_t e_bin0, e_bin1, e_plan1, e_cnt0, e_cnt1, e_sel1, e_asc1;
     uint64_t* o_sig; float* o_score; int64_t* o_niso; int32_t* o_nsites; float* o_asc; uint64_t* o_alt; int32_t* o_status;
+    bool single_chunk = false;       // the call has one chunk
+    bool packed = false;             // inputs / outputs travel as one block each (small host batch)
+    std::vector<PackOut> pack_out;
+    size_t pack_out_bytes = 0;
 };
 
 struct ChunkEnds { int64_t peak_lo, peak_hi, pep_lo, pep_hi; };   // range ends of a device-resident chunk
@@ -710,10 +751,35 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     cs.r = r; cs.mod_lo = mod_lo; cs.mod_hi = mod_hi;
     int64_t* h2d = &s->ctr.bytes_h2d;
     PaBatchDev& b = cs.b;
-    const double *v_mz, *v_int;
+    const double *v_mz, *v_int = nullptr;
+    const float* v_int32 = nullptr;
+    const int64_t n_aux = aux_hi - aux_lo;
+    const size_t pack_bytes = (size_t)(ns + 1) * 8 + (size_t)npk * (in->inten32 ? 12 : 16) + (size_t)np * 12 + (size_t)(np + 1) * 16 +
+                              (size_t)(pep_hi - pep_lo) + (size_t)n_aux * 8 + 16 * 16;
+    cs.packed = !in_dev && cs.single_chunk && pack_bytes <= PA_PACK_MAX;
+    if (cs.packed) {
+        CK(ensure_pinned(sl.h_pack, sl.h_pack_cap, pack_bytes));
+        CK(sl.d_pack.ensure(pack_bytes));
+        PackIn pk{sl.h_pack, sl.d_pack.as<unsigned char>(), 0};
+        b.spec_off = pk.add(in->spec_off, r.s0, ns + 1);
+        v_mz = pk.add(in->mz, peak_lo, npk);
+        if (in->inten32) v_int32 = pk.add(in->inten32, peak_lo, npk); else v_int = pk.add(in->inten, peak_lo, npk);
+        b.psm_spec = pk.add(in->psm_spec, r.p0, np);
+        b.pep_off = pk.add(in->pep_off, r.p0, np + 1);
+        b.pep = pk.add(in->pep, pep_lo, pep_hi - pep_lo);
+        b.n_mod = pk.add(in->n_mod, r.p0, np);
+        b.max_charge = pk.add(in->max_charge, r.p0, np);
+        b.aux_off = pk.add(in->aux_off, r.p0, np + 1);
+        b.aux_pos = in->aux_off ? pk.add(in->aux_pos, aux_lo, n_aux) : nullptr;
+        b.aux_mass = in->aux_off ? pk.add(in->aux_mass, aux_lo, n_aux) : nullptr;
+        cs.mod_off_abs = pk.add(in->mod_off, r.p0, np + 1);
+        CK(cudaMemcpyAsync(sl.d_pack.p, sl.h_pack, pk.used, cudaMemcpyHostToDevice, st));
+        *h2d += (int64_t)pk.used;
+    } else {
     CK(stage_in(sl.spec_off, in->spec_off, in_dev, r.s0, ns + 1, st, &b.spec_off, h2d));
     CK(stage_in(sl.mz, in->mz, in_dev, peak_lo, npk, st, &v_mz, h2d));
-    CK(stage_in(sl.inten, in->inten, in_dev, peak_lo, npk, st, &v_int, h2d));
+    if (in->inten32) CK(stage_in(sl.inten32, in->inten32, in_dev, peak_lo, npk, st, &v_int32, h2d));
+    else CK(stage_in(sl.inten, in->inten, in_dev, peak_lo, npk, st, &v_int, h2d));
     CK(stage_in(sl.psm_spec, in->psm_spec, in_dev, r.p0, np, st, &b.psm_spec, h2d));
     CK(stage_in(sl.pep_off, in->pep_off, in_dev, r.p0, np + 1, st, &b.pep_off, h2d));
     CK(stage_in(sl.pep, in->pep, in_dev, pep_lo, pep_hi - pep_lo, st, &b.pep, h2d));
@@ -725,6 +791,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
         CK(stage_in(sl.aux_mass, in->aux_mass, in_dev, aux_lo, aux_hi - aux_lo, st, &b.aux_mass, h2d));
     } else { b.aux_pos = nullptr; b.aux_mass = nullptr; }
     CK(stage_in(sl.mod_off, in->mod_off, in_dev, r.p0, np + 1, st, &cs.mod_off_abs, h2d));
+    }
     // PSM-indexed views become chunk-relative
     b.psm_spec += r.p0; b.pep_off += r.p0; b.n_mod += r.p0; b.max_charge += r.p0;
     if (b.aux_off) b.aux_off += r.p0;
@@ -740,7 +807,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     CK(sl.chead.ensure((size_t)std::max<int64_t>(ns, 1) * sizeof(float2)));
     PaBinArgs ba;
     ba.spec_off = b.spec_off + r.s0;          // kernel indexes spectra 0..ns-1
-    ba.mz = v_mz; ba.inten = v_int; ba.peak_base = 0; ba.n_spec = ns;
+    ba.mz = v_mz; ba.inten = v_int; ba.inten32 = v_int32; ba.peak_base = 0; ba.n_spec = ns;
     ba.rpk = sl.rpk.as<float2>() - peak_lo; ba.rmz = nullptr; ba.rrank = nullptr;
     ba.g_bin = sl.g_bin.as<int32_t>() - peak_lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - peak_lo;
     ba.rcount = sl.rcount.as<int32_t>();
@@ -755,7 +822,8 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     cs.e_bin0 = next_event(s); cs.e_bin1 = next_event(s); cs.e_plan1 = next_event(s);
     CK(cudaEventRecord(cs.e_bin0, st));
     if (ns > 0) {
-        k_bin_topn<<<std::max(blocks, 1), wpb * 32, smem, st>>>(ba);
+        if (ba.inten32) k_bin_topn<true><<<std::max(blocks, 1), wpb * 32, smem, st>>>(ba);
+        else k_bin_topn<false><<<std::max(blocks, 1), wpb * 32, smem, st>>>(ba);
         CK(cudaGetLastError());
         s->ctr.kernel_launches++; s->ctr.launches_bin++;
     }
@@ -871,6 +939,34 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     }
     CK(cudaEventRecord(cs.e_cnt1, st));
     // outputs
+    const int64_t nm = cs.mod_hi - cs.mod_lo;
+    const bool pack_results = cs.packed && !out_dev && (size_t)np * 32 + (size_t)nm * 12 + 8 * 16 <= PA_PACK_MAX;
+    if (pack_results) {
+        size_t used = 0;
+        auto slot_of = [&](void* dst, int64_t lo, int64_t n, size_t elem) -> unsigned char* {      // view with absolute indices
+            if (!dst) return nullptr;
+            const size_t off = (used + 15) & ~(size_t)15;
+            used = off + (size_t)std::max<int64_t>(n, 0) * elem;
+            cs.pack_out.push_back({off, (size_t)std::max<int64_t>(n, 0) * elem, (unsigned char*)dst + (size_t)lo * elem});
+            return (unsigned char*)nullptr + off - (size_t)lo * elem;      // offset relative to the block, rebased below
+        };
+        const size_t bound = (size_t)np * 32 + (size_t)nm * 12 + 8 * 16;
+        CK(sl.d_opack.ensure(bound));
+        CK(ensure_pinned(sl.h_opack, sl.h_opack_cap, bound));
+        unsigned char* base = sl.d_opack.as<unsigned char>();
+        auto rebase = [&](unsigned char* rel) { return rel == nullptr ? nullptr : base + (size_t)(rel - (unsigned char*)nullptr); };
+        // (a NULL result pointer means "skip": slot_of returns nullptr and so does rebase -- but an offset of 0 must
+        // not be mistaken for it, so the block starts with 16 bytes of padding)
+        used = 16;
+        cs.o_sig = (uint64_t*)rebase(slot_of(out->best_sig, r.p0, np, 8));
+        cs.o_score = (float*)rebase(slot_of(out->best_score, r.p0, np, 4));
+        cs.o_niso = (int64_t*)rebase(slot_of(out->n_iso, r.p0, np, 8));
+        cs.o_nsites = (int32_t*)rebase(slot_of(out->n_sites, r.p0, np, 4));
+        cs.o_asc = (float*)rebase(slot_of(out->ascores, cs.mod_lo, nm, 4));
+        cs.o_alt = (uint64_t*)rebase(slot_of(out->alt_sites, cs.mod_lo, nm, 8));
+        cs.o_status = (int32_t*)rebase(slot_of(out->psm_status, r.p0, np, 4));
+        cs.pack_out_bytes = used;
+    } else {
     CK(stage_out(sl.o_sig, out->best_sig, out_dev, r.p0, np, &cs.o_sig));
     CK(stage_out(sl.o_score, out->best_score, out_dev, r.p0, np, &cs.o_score));
     CK(stage_out(sl.o_niso, out->n_iso, out_dev, r.p0, np, &cs.o_niso));
@@ -878,7 +974,7 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     CK(stage_out(sl.o_asc, out->ascores, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, &cs.o_asc));
     CK(stage_out(sl.o_alt, out->alt_sites, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, &cs.o_alt));
     CK(stage_out(sl.o_status, out->psm_status, out_dev, r.p0, np, &cs.o_status));
-    const int64_t nm = cs.mod_hi - cs.mod_lo;
+    }
     CK(sl.best_idx.ensure((size_t)std::max<int64_t>(np, 1) * 4));
     CK(sl.mod_psm.ensure((size_t)std::max<int64_t>(nm, 1) * 4));
     CK(sl.tie.ensure((size_t)std::max<int64_t>(nm, 1) * 8));
@@ -942,52 +1038,31 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
                                            sl.work_val.as<int32_t>(), sl.work_sorted.as<int32_t>(), (int)nm, 0, PA_WORK_BITS, st));
         s->ctr.kernel_launches += 3;
         const unsigned ab = (unsigned)((nm + 127) / 128);
-        if (s->asc_form == 3) {
-            // pairs (entry, tied competitor) numbered by a scan over the sorted entry list, handed out from a cursor
-            CK(sl.item_cnt.ensure((size_t)(nm + 1) * 4)); CK(sl.item_off.ensure((size_t)(nm + 1) * 4));
-            CK(sl.gen_flag.ensure((size_t)nm * 4));
-            CK(sl.asc_cursor.ensure(32));
-            CK(cudaMemsetAsync(sl.gen_flag.p, 0, (size_t)nm * 4, st));
-            CK(cudaMemsetAsync(sl.asc_cursor.p, 0, 32, st));
-            PaAscItemArgs ia;
-            ia.item_cnt = sl.item_cnt.as<int32_t>(); ia.item_off = sl.item_off.as<int32_t>();
-            ia.cursor = sl.asc_cursor.as<unsigned long long>(); ia.gen_flag = sl.gen_flag.as<int>();
-            k_asc_item_count<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(aa, ia);
-            size_t ts = 0;
-            CK(cub::DeviceScan::ExclusiveSum(nullptr, ts, ia.item_cnt, sl.item_off.as<int32_t>(), (int)(nm + 1), st));
-            CK(sl.cub_tmp.ensure(ts + 256));
-            ts = sl.cub_tmp.cap;
-            CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, ts, ia.item_cnt, sl.item_off.as<int32_t>(), (int)(nm + 1), st));
-            s->ctr.kernel_launches += 2;
+        // pairs (entry, tied competitor) numbered by a scan over the sorted entry list, handed out from a cursor
+        CK(sl.item_cnt.ensure((size_t)(nm + 1) * 4)); CK(sl.item_off.ensure((size_t)(nm + 1) * 4));
+        CK(sl.gen_flag.ensure((size_t)nm * 4));
+        CK(sl.asc_cursor.ensure(32));
+        CK(cudaMemsetAsync(sl.gen_flag.p, 0, (size_t)nm * 4, st));
+        CK(cudaMemsetAsync(sl.asc_cursor.p, 0, 32, st));
+        PaAscItemArgs ia;
+        ia.item_cnt = sl.item_cnt.as<int32_t>(); ia.item_off = sl.item_off.as<int32_t>();
+        ia.cursor = sl.asc_cursor.as<unsigned long long>(); ia.gen_flag = sl.gen_flag.as<int>();
+        k_asc_item_count<<<(unsigned)((nm + 1 + 255) / 256), 256, 0, st>>>(aa, ia);
+        size_t ts = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, ts, ia.item_cnt, sl.item_off.as<int32_t>(), (int)(nm + 1), st));
+        CK(sl.cub_tmp.ensure(ts + 256));
+        ts = sl.cub_tmp.cap;
+        CK(cub::DeviceScan::ExclusiveSum(sl.cub_tmp.p, ts, ia.item_cnt, sl.item_off.as<int32_t>(), (int)(nm + 1), st));
+        s->ctr.kernel_launches += 2;
 #define PA_PAIRS_LAUNCH(NQ, CLS, SMEM) { \
-                const int blocks = (int)std::min<int64_t>(ab, (int64_t)s->sm_count * resident_blocks(k_ascore_pairs<NQ, CLS>, 128, SMEM)); \
-                k_ascore_pairs<NQ, CLS><<<blocks, 128, SMEM, st>>>(s->cfg, cs.b, aa, ia); }
-            if (!s->cfg.has_nl) {
-                PA_PAIRS_LAUNCH(1, 0, 0) PA_PAIRS_LAUNCH(2, 1, 0) PA_PAIRS_LAUNCH(4, 2, 0)
-                s->ctr.kernel_launches += 3;
-            }
-            PA_PAIRS_LAUNCH(PA_MAXSTREAM, 3, sizeof(AscSm))
-#undef PA_PAIRS_LAUNCH
-        } else if (s->asc_form == 1) {
-            if (!s->cfg.has_nl) {
-                k_ascore<1, 0><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
-                k_ascore<2, 1><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
-                k_ascore<4, 2><<<ab, 128, 0, st>>>(s->cfg, cs.b, aa);
-                s->ctr.kernel_launches += 3;
-            }
-            k_ascore<PA_MAXSTREAM, 3><<<ab, ASC_BLOCK, sizeof(AscSm), st>>>(s->cfg, cs.b, aa);
-        } else {
-            // one warp per 32 entries of the work-sorted list (longest merges first: the block scheduler hands
-            // them out in that order); the entry count of a class is only known on the device
-            if (!s->cfg.has_nl) {
-                k_ascore_items<1, 0, false><<<ab, ASC_BLOCK, sizeof(AscSm2<1, false>), st>>>(s->cfg, cs.b, aa);
-                k_ascore_items<2, 1, false><<<ab, ASC_BLOCK, sizeof(AscSm2<2, false>), st>>>(s->cfg, cs.b, aa);
-                k_ascore_items<4, 2, false><<<ab, ASC_BLOCK, sizeof(AscSm2<4, false>), st>>>(s->cfg, cs.b, aa);
-                k_ascore_items<PA_MAXSTREAM, 3, false><<<ab, ASC_BLOCK, sizeof(AscSm2<PA_MAXSTREAM, false>), st>>>(s->cfg, cs.b, aa);
-                s->ctr.kernel_launches += 3;
-            } else
-                k_ascore_items<PA_MAXSTREAM, 3, true><<<ab, ASC_BLOCK, sizeof(AscSm2<PA_MAXSTREAM, true>), st>>>(s->cfg, cs.b, aa);
+            const int blocks = (int)std::min<int64_t>(ab, (int64_t)s->sm_count * resident_blocks(k_ascore_pairs<NQ, CLS>, 128, SMEM)); \
+            k_ascore_pairs<NQ, CLS><<<blocks, 128, SMEM, st>>>(s->cfg, cs.b, aa, ia); }
+        if (!s->cfg.has_nl) {
+            PA_PAIRS_LAUNCH(1, 0, 0) PA_PAIRS_LAUNCH(2, 1, 0) PA_PAIRS_LAUNCH(4, 2, 0)
+            s->ctr.kernel_launches += 3;
         }
+        PA_PAIRS_LAUNCH(PA_MAXSTREAM, 3, sizeof(AscSm))
+#undef PA_PAIRS_LAUNCH
         CK(cudaGetLastError());
         const int wpb = 8;
         int blocks = s->sm_count * 2;
@@ -1000,6 +1075,10 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     }
     CK(cudaEventRecord(cs.e_asc1, st));
     int64_t* d2h = &s->ctr.bytes_d2h;
+    if (pack_results) {
+        CK(cudaMemcpyAsync(sl.h_opack, sl.d_opack.p, cs.pack_out_bytes, cudaMemcpyDeviceToHost, st));
+        *d2h += (int64_t)cs.pack_out_bytes;
+    } else {
     CK(copy_out(sl.o_sig, out->best_sig, out_dev, r.p0, np, st, d2h));
     CK(copy_out(sl.o_score, out->best_score, out_dev, r.p0, np, st, d2h));
     CK(copy_out(sl.o_niso, out->n_iso, out_dev, r.p0, np, st, d2h));
@@ -1007,6 +1086,7 @@ static int chunk_back(pa_scorer* s, int si, const pa_results* out, bool out_dev,
     CK(copy_out(sl.o_asc, out->ascores, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, st, d2h));
     CK(copy_out(sl.o_alt, out->alt_sites, out_dev, cs.mod_lo, cs.mod_hi - cs.mod_lo, st, d2h));
     CK(copy_out(sl.o_status, out->psm_status, out_dev, r.p0, np, st, d2h));
+    }
     s->ctr.n_isoforms += total_iso;
     if (keep) {
         s->kept.b = cs.b; s->kept.n_psm = np; s->kept.psm_lo = r.p0;
@@ -1039,7 +1119,7 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
     if (s->binner_only) return fail(s, PA_ERR_STATE, "this handle was made by pa_create_binner: it only bins spectra");
     if (in->n_psm < 0 || in->n_spec < 0) return fail(s, PA_ERR_ARG, "negative sizes");
     if (p_lo < 0 || p_hi > in->n_psm || p_lo > p_hi) return fail(s, PA_ERR_ARG, "PSM range [%lld, %lld) outside the batch of %lld", (long long)p_lo, (long long)p_hi, (long long)in->n_psm);
-    if (in->n_psm > 0 && (!in->spec_off || !in->mz || !in->inten || !in->psm_spec || !in->pep_off || !in->pep ||
+    if (in->n_psm > 0 && (!in->spec_off || !in->mz || (!in->inten && !in->inten32) || !in->psm_spec || !in->pep_off || !in->pep ||
                           !in->n_mod || !in->max_charge || !in->mod_off))
         return fail(s, PA_ERR_ARG, "NULL input array");
     CK(cudaSetDevice(s->device));
@@ -1111,51 +1191,63 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
             s->ctr.n_peaks += e.peak_hi - e.peak_lo;
         }
     } else {
-        bool mono = true;
-        for (int64_t p = p_lo + 1; p < p_hi && mono; p++) mono = in->psm_spec[p] >= in->psm_spec[p - 1];
-        for (int64_t p = p_lo; p < p_hi && mono; p++) mono = in->psm_spec[p] >= 0 && in->psm_spec[p] < in->n_spec;
+        // one branch-free pass (the compiler vectorises it): PSMs in spectrum order, indices in range
+        int bad = 0;
+        {
+            const int32_t* ps = in->psm_spec;
+            const int32_t ns = (int32_t)std::min<int64_t>(in->n_spec, INT32_MAX);
+            bad |= (ps[p_lo] < 0) | (ps[p_lo] >= ns);
+            for (int64_t p = p_lo + 1; p < p_hi; p++) bad |= (ps[p] < ps[p - 1]) | (ps[p] >= ns);
+        }
+        const bool mono = bad == 0;
         if (!mono || keep) chunks.push_back({p_lo, p_hi, mono ? (int64_t)in->psm_spec[p_lo] : 0, mono ? (int64_t)in->psm_spec[p_hi - 1] + 1 : in->n_spec});
         else {
+            // about eight chunks per call (copy of chunk c+1 under the kernels of chunk c), never beyond PA_CHUNK_PSM PSMs
+            // or PA_CHUNK_PEAKS peaks; small ranges (one GPU's share of a sharded batch) get small chunks
+            const int64_t per = std::min<int64_t>(PA_CHUNK_PSM, std::max<int64_t>(PA_CHUNK_MIN, ((n_range + 7) / 8 + 1023) / 1024 * 1024));
             int64_t p0 = p_lo;
             while (p0 < p_hi) {
                 int64_t s0 = in->psm_spec[p0];
                 // PSMs sharing the spectrum of p0 that were cut off by the previous chunk stay reachable:
                 // chunk spectra start at the first spectrum referenced
-                int64_t p1 = std::min<int64_t>(p0 + PA_CHUNK_PSM, p_hi);
+                int64_t p1 = std::min<int64_t>(p0 + per, p_hi);
                 while (p1 > p0 + 1 && in->spec_off[in->psm_spec[p1 - 1] + 1] - in->spec_off[s0] > PA_CHUNK_PEAKS) p1 = p0 + (p1 - p0) / 2;
                 int64_t s1 = (int64_t)in->psm_spec[p1 - 1] + 1;
                 chunks.push_back({p0, p1, s0, s1});
                 p0 = p1;
             }
         }
-        if (!mono) {        // spectrum indices were not validated by the scan above: the plan kernel flags them per PSM
-            const char* why = check_host_range(in, p_lo, p_hi, 0, in->n_spec);
-            if (why) return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why);
-        }
-        for (auto& c : chunks) {
-            if (mono) {
-                const char* why = (&c == &chunks[0]) ? check_host_range(in, c.p0, c.p1, c.s0, c.s1) : nullptr;
-                if (why) return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why);
-            }
-            int64_t m = 0;
-            for (int64_t q = c.s0; q < c.s1; q++) m = std::max<int64_t>(m, in->spec_off[q + 1] - in->spec_off[q]);
-            chunk_maxp.push_back((int)std::min<int64_t>(std::max<int64_t>(m, 0), 1 << 20));
-            mod_lo.push_back(in->mod_off[c.p0]); mod_hi.push_back(in->mod_off[c.p1]);
-            s->ctr.n_peaks += in->spec_off[c.s1] - in->spec_off[c.s0];
-        }
+        chunk_maxp.assign(chunks.size(), 0); mod_lo.assign(chunks.size(), 0); mod_hi.assign(chunks.size(), 0);
     }
-    const bool check_chunks = !in_dev && chunks.size() > 1;      // chunk 0 was checked above
+    // per-chunk host work of a host batch, done right before the chunk is staged (so that all but the first chunk's
+    // share overlaps the GPU): consistency of the CSR arrays, largest spectrum, range in the per-mod outputs
+    auto prepare_host_chunk = [&](size_t c) -> const char* {
+        const ChunkRange& r = chunks[c];
+        const char* why = check_host_range(in, r.p0, r.p1, r.s0, r.s1);
+        if (why) return why;
+        int64_t m = 0;
+        for (int64_t q = r.s0; q < r.s1; q++) m = std::max<int64_t>(m, in->spec_off[q + 1] - in->spec_off[q]);
+        chunk_maxp[c] = (int)std::min<int64_t>(std::max<int64_t>(m, 0), 1 << 20);
+        mod_lo[c] = in->mod_off[r.p0]; mod_hi[c] = in->mod_off[r.p1];
+        s->ctr.n_peaks += in->spec_off[r.s1] - in->spec_off[r.s0];
+        return nullptr;
+    };
+    if (!in_dev) {
+        const char* why = prepare_host_chunk(0);
+        if (why) return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why);
+    }
+    const bool check_chunks = !in_dev && chunks.size() > 1;      // chunk 0 was prepared above
 
     // ---- two-slot software pipeline ----
     std::vector<ChunkState> cs(chunks.size());
     s->ctr.n_chunks = (int64_t)chunks.size();
+    cs[0].single_chunk = chunks.size() == 1;
     rc = chunk_front(s, 0, in, in_dev, chunks[0], mod_lo[0], mod_hi[0], chunk_maxp[0], cs[0], in_dev ? &ends_dev[0] : nullptr);
     if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
     for (size_t c = 0; c < chunks.size(); c++) {
         if (c + 1 < chunks.size()) {
             if (check_chunks) {
-                const ChunkRange& n = chunks[c + 1];
-                const char* why = check_host_range(in, n.p0, n.p1, n.s0, n.s1);
+                const char* why = prepare_host_chunk(c + 1);
                 if (why) { cudaDeviceSynchronize(); return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why); }
             }
             // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
@@ -1172,6 +1264,9 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
     CK(cudaStreamSynchronize(s->slot[1].st));
     CK(cudaEventRecord(e_all1, s->slot[0].st));
     CK(cudaEventSynchronize(e_all1));
+    for (size_t c = 0; c < chunks.size(); c++)       // packed results: from the pinned block into the caller's arrays
+        for (const PackOut& po : cs[c].pack_out)
+            if (po.bytes) memcpy(po.dst, s->slot[c & 1].h_opack + po.off, po.bytes);
     // counters
     for (size_t c = 0; c < chunks.size(); c++) {
         float ms = 0.f;
@@ -1440,7 +1535,7 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     int64_t m = 0;
     for (int64_t q = 0; q < n_spec; q++) m = std::max<int64_t>(m, spec_off[q + 1] - spec_off[q]);
     PaBinArgs ba;
-    ba.spec_off = v_off; ba.mz = v_mz; ba.inten = v_int; ba.peak_base = 0; ba.n_spec = n_spec;
+    ba.spec_off = v_off; ba.mz = v_mz; ba.inten = v_int; ba.inten32 = nullptr; ba.peak_base = 0; ba.n_spec = n_spec;
     ba.rpk = sl.rpk.as<float2>() - lo; ba.rmz = sl.rmz.as<float>() - lo; ba.rrank = sl.rrank.as<uint8_t>() - lo;
     ba.g_bin = sl.g_bin.as<int32_t>() - lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - lo;
     ba.rcount = sl.rcount.as<int32_t>(); ba.bin_size = s->bin_size; ba.n_top = s->n_top;
@@ -1452,7 +1547,7 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     size_t smem;
     bin_launch_shape(s->sm_count, m, n_spec, &cap, &wpb, &smem, &blocks);
     ba.cap = cap;
-    k_bin_topn<<<blocks, wpb * 32, smem, st>>>(ba);
+    k_bin_topn<false><<<blocks, wpb * 32, smem, st>>>(ba);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_mz + lo, sl.rmz.p, (size_t)npk * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_rank + lo, sl.rrank.p, (size_t)npk, cudaMemcpyDeviceToHost, st));

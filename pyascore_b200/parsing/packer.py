@@ -94,7 +94,7 @@ class PsmPacker:
         np.cumsum([a.size for a in self.aux_pos], out=aux_off[1:])
         sp = self.spectra
         batch = dict(
-            spec_off=sp.spec_off, mz=sp.mz, inten=sp.inten,
+            spec_off=sp.spec_off, mz=sp.mz, **({"inten": sp.inten} if sp.inten is not None else {"inten32": sp.inten32}),
             psm_spec=np.array(self.psm_spec, np.int32), pep_off=pep_off,
             pep=np.frombuffer(b"".join(self.peps), np.uint8).copy() if n else np.zeros(0, np.uint8),
             n_mod=np.array(self.n_mod, np.int32), max_charge=np.array(self.max_charge, np.int32), aux_off=aux_off,
@@ -124,28 +124,43 @@ def score_stream(scorer, batches, depth=2):
 
     `pa_score_batch` is a blocking C call that releases the GIL (ctypes), so host-side
     parsing/packing of chunk c+1 overlaps the H2D copies and kernels of chunk c.  Yields
-    (scans, batch, results) in order."""
+    (scans, batch, results) in order.  If scoring raises or the consumer abandons the generator,
+    the producer is told to stop and joined, so no thread is left blocked on the bounded queue."""
     q = queue.Queue(maxsize=depth)
+    stop = threading.Event()
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def producer():
         try:
             for item in batches:
-                q.put(item)
-            q.put(None)
+                if not put(item):
+                    return
+            put(None)
         except BaseException as e:      # surfaced in the consumer
-            q.put(e)
+            put(e)
 
     t = threading.Thread(target=producer, daemon=True)
     t.start()
-    while True:
-        item = q.get()
-        if item is None:
-            break
-        if isinstance(item, BaseException):
-            raise item
-        scans, batch = item
-        yield scans, batch, scorer.score_batch(batch)
-    t.join()
+    try:
+        while True:
+            item = q.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            scans, batch = item
+            yield scans, batch, scorer.score_batch(batch)
+    finally:
+        stop.set()
+        t.join(timeout=30)
 
 
 def result_rows(scorer, scans, batch, res):

@@ -16,13 +16,14 @@ _READERS = {"mzML": _xml.iter_mzml, "mzXML": _xml.iter_mzxml}
 class SpectraCSR:
     """All retained scans of one file: scans ascending, peaks of scan i at mz[spec_off[i]:spec_off[i+1]]."""
 
-    def __init__(self, scans, precursor_mz, precursor_charge, spec_off, mz, inten):
+    def __init__(self, scans, precursor_mz, precursor_charge, spec_off, mz, inten, inten32=None):
         self.scans = scans                          # int64[n_spec], ascending
         self.precursor_mz = precursor_mz            # float64[n_spec], NaN = missing
         self.precursor_charge = precursor_charge    # int32[n_spec], 0 = missing
         self.spec_off = spec_off                    # int64[n_spec+1]
         self.mz = mz                                # float64[n_peaks]  (pinned when a GPU library is loaded)
-        self.inten = inten
+        self.inten = inten                          # float64[n_peaks], or None when every intensity of the file is a
+        self.inten32 = inten32                      #   float32 value: then float32[n_peaks] here (pa_batch.inten32)
         self._index = None
 
     def __len__(self):
@@ -36,7 +37,7 @@ class SpectraCSR:
 
     def spectrum(self, i):
         a, b = int(self.spec_off[i]), int(self.spec_off[i + 1])
-        return self.mz[a:b], self.inten[a:b]
+        return self.mz[a:b], (self.inten if self.inten is not None else self.inten32)[a:b]
 
 
 class SpectraParser:
@@ -78,22 +79,31 @@ class SpectraParser:
         return self._spectra
 
     def to_dict(self):
-        """{scan number : spectrum}; like the reference this pops "scan" out of the cached records"""
+        """{scan number : spectrum without its "scan" key} (the reference pops the key out of its cached records,
+        spec_parsers.py:281, so a second call fails there; the cache is left intact here)"""
         self._get_spectra()
-        return {spec.pop("scan"): spec for spec in self._spectra}
+        return {spec["scan"]: {k: v for k, v in spec.items() if k != "scan"} for spec in self._spectra}
 
-    def to_csr(self, pinned=True):
-        """Pack the retained scans into one CSR block (pinned host memory by default)."""
-        recs = sorted(self._records(), key=lambda s: s["scan"]) if not self._spectra else self._spectra
+    def to_csr(self, pinned=True, narrow_intensity=True):
+        """Pack the retained scans into one CSR block (pinned host memory by default).
+
+        narrow_intensity: when every intensity of the file is exactly a float32 value (mzML / mzXML files usually
+        store 32-bit intensity arrays) the block carries them as float32 (`inten32`, `inten` = None): a quarter
+        fewer bytes over the host link, same ranks (pa_batch.inten32)."""
+        self._get_spectra()
+        recs = self._spectra
         n = len(recs)
         spec_off = np.zeros(n + 1, np.int64)
         np.cumsum([r["mz_values"].size for r in recs], out=spec_off[1:])
         total = int(spec_off[-1])
+        narrow = narrow_intensity and total > 0 and all(
+            np.array_equal(r["intensity_values"].astype(np.float32), r["intensity_values"]) for r in recs)
+        idt = np.float32 if narrow else np.float64
         if pinned:
             from ..batch import pinned_empty
-            mz, inten = pinned_empty(total, np.float64), pinned_empty(total, np.float64)
+            mz, inten = pinned_empty(total, np.float64), pinned_empty(total, idt)
         else:
-            mz, inten = np.empty(total, np.float64), np.empty(total, np.float64)
+            mz, inten = np.empty(total, np.float64), np.empty(total, idt)
         for i, r in enumerate(recs):
             a, b = spec_off[i], spec_off[i + 1]
             mz[a:b] = r["mz_values"]
@@ -101,4 +111,4 @@ class SpectraParser:
         scans = np.array([r["scan"] for r in recs], np.int64)
         pmz = np.array([np.nan if r["precursor_mz"] is None else r["precursor_mz"] for r in recs], np.float64)
         pz = np.array([0 if r["precursor_charge"] is None else r["precursor_charge"] for r in recs], np.int32)
-        return SpectraCSR(scans, pmz, pz, spec_off, mz, inten)
+        return SpectraCSR(scans, pmz, pz, spec_off, mz, None if narrow else inten, inten if narrow else None)

@@ -179,3 +179,44 @@ def test_config1_cli_sharded(tmp_path):
     for setting in ("default", "hires_nl"):
         main(_argv(expected[setting]["args"]) + ["--devices", devs, spec, ident, out])
         _compare(open(out).read(), expected[setting]["tsv"])
+
+
+@pytest.mark.parametrize("workload,n", WORKLOADS)
+def test_float32_intensities_equal_float64(workload, n):
+    """pa_batch.inten32: float32 intensities give, bit for bit, what the same values give as float64 (the ranking
+    only compares them); covered on sorted spectra, on a permuted one (general binning path) and with exact ties"""
+    batch = synth.make_batch(workload, n, seed=77, chunk_index=4)
+    i32 = batch["inten"].astype(np.float32)
+    a, b = int(batch["spec_off"][3]), int(batch["spec_off"][4])
+    i32[a:a + 6] = i32[a]                                            # ties inside a bin: earlier peak wins, both ways
+    perm = np.random.default_rng(1).permutation(b - a)               # spectrum 3 unsorted -> the general path
+    batch["mz"][a:b] = batch["mz"][a:b][perm]
+    i32[a:b] = i32[a:b][perm]
+    b64 = dict(batch, inten=i32.astype(np.float64))
+    b32 = {k: v for k, v in batch.items() if k != "inten"}
+    b32["inten32"] = i32
+    s = _scorer(workload)
+    r64 = s.score_batch(b64)
+    r32 = s.score_batch(b32)
+    assert _same(r64, r32)
+    assert s.counters()["bytes_h2d"] < 0.8 * (batch["mz"].nbytes * 2)
+    import torch
+    dev = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda() for k, v in b32.items()}
+    rd = s.score_batch(dev)
+    assert all(rd[k].cpu().numpy().tobytes() == np.asarray(r64[k]).tobytes() for k in r64)
+    s.close()
+
+
+def test_spectra_block_narrows_float32_intensities(tmp_path):
+    """SpectraParser.to_csr hands float32 intensities over when the file's values are float32 (and only then)"""
+    from pyascore_b200.parsing import SpectraParser
+    spectra, _, _ = load_config1()
+    p32, p64 = str(tmp_path / "a.mzML"), str(tmp_path / "b.mzML")
+    _msfiles.write_mzml(p32, spectra, inten_bits=32)
+    wide = [dict(sp, inten=sp["inten"].astype(np.float64) * (1. + 1e-12)) for sp in spectra]
+    _msfiles.write_mzml(p64, wide, inten_bits=64)
+    c32 = SpectraParser(p32, "mzML").to_csr()
+    c64 = SpectraParser(p64, "mzML").to_csr()
+    assert c32.inten is None and c32.inten32.dtype == np.float32
+    assert c64.inten32 is None and c64.inten.dtype == np.float64
+    assert np.array_equal(c32.inten32.astype(np.float64), SpectraParser(p32, "mzML").to_csr(narrow_intensity=False).inten)
