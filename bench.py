@@ -775,7 +775,7 @@ def run_config(name, batch, n_dev, args, peak, peak_src, clocks, sm_count, torch
                 "d2h_bytes_per_step": int(sum(c["bytes_d2h"] for c in ctrs)), "h2d_achieved_gbs": h2d / e2e_s / 1e9,
                 "timing": "wall clock around MultiScorer.score_batch (cut + every range), one process, pinned host arrays",
                 "pinned_pages": policy, "placements_tried": tried},
-        "shard_psms": [b - a for a, b in ranges],
+        "shard_psms": [b - a for a, b in ranges], "shard_share": [float(x) for x in ms.share / ms.share.sum()],
         "shard_ms_cuda_events": [c["ms_total"] for c in ctrs],
         "kernel_ms_per_step_gpu0": kernel_ms(ctr0),
         "roofline_gpu0": roofline_of(name, shards[0], int(shards[0]["mod_off"][-1]), ctr0, peak, peak_src, clocks, sm_count),

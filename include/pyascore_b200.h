@@ -48,7 +48,13 @@ enum {
     PA_PSM_TOO_MANY_FRAGMENTS = 8 /* theoretical fragments per isoform exceed PA_MAX_FRAGMENTS */
 };
 
-#define PA_N_TOP 10               /* peak depth: the reference's weight vector has 10 entries (cpp/Ascore.cpp:15-19) */
+/* Peak depth of a scoring handle.  The reference's weight vector has 10 entries (cpp/Ascore.cpp:15-19): n_top < 10 reads
+ * out of bounds there; for n_top > 10 the PepScores, the isoform order, best_sequence and the alternative sites are
+ * those of n_top = 10 (deeper ranks only add count / score columns and can move the depth calculateAmbiguity picks,
+ * cpp/Ascore.cpp:165-175 -- shown on the compiled reference by tests/test_oracle_vs_ref.py::
+ * test_reference_behaviour_for_n_top_above_10).  pa_create therefore takes n_top = 10 only -- the value
+ * pyascore/__main__.py:69 hard-codes -- and reports anything else as PA_ERR_UNSUPPORTED. */
+#define PA_N_TOP 10
 #define PA_MAX_PEPTIDE 126
 #define PA_MAX_SITES 63
 #define PA_MAX_ISOFORMS (1ll << 26)
@@ -139,12 +145,15 @@ int pa_wait(pa_scorer* s);
  * cuts[world] = n_psm, rank r takes PSMs [cuts[r], cuts[r+1]).  psm_spec must be non-decreasing (scan-sorted PSMs,
  * as pyascore/__main__.py:38-44 sorts them); cuts never split the hits of one spectrum.  Ranges are balanced by
  * estimated cost: isoforms x fragments + peak_weight x peaks of the spectrum / its hits (peak_weight ~ 55 for host
- * inputs, where the host -> device copy of the peaks dominates; ~ 4 for kernel time alone).  Host arithmetic only. */
-int pa_shard_ranges(const pa_scorer* s, const pa_batch* in, int32_t world, double peak_weight, int64_t* cuts);
+ * inputs, where the host -> device copy of the peaks dominates; ~ 4 for kernel time alone).  `share` (NULL = equal) gives
+ * rank r the fraction share[r] / sum(share) of the cost: when every GPU of a box copies at once they do not all get the
+ * same host-link bandwidth (measured: 23 vs 35 GB/s on the two halves of an 8-GPU box).  Host arithmetic only. */
+int pa_shard_ranges(const pa_scorer* s, const pa_batch* in, int32_t world, double peak_weight, const double* share,
+                    int64_t* cuts);
 /* The same without a scorer handle (no GPU needed): mod_group as given to pa_create, the number of ion types and
  * the largest neutral-loss variant count per residue (1 without neutral losses). */
 int pa_shard_ranges_for(const char* mod_group, int32_t n_types, int32_t nl_variants, const pa_batch* in,
-                        int32_t world, double peak_weight, int64_t* cuts);
+                        int32_t world, double peak_weight, const double* share, int64_t* cuts);
 
 /* Replaces the pep_scores property (Ascore.pyx:240-252 -> cpp/Ascore.cpp:281-303) for PSM
  * `psm` of the last batch scored with PA_KEEP_ISOFORMS.  Rows come in the reference's order

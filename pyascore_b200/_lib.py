@@ -78,9 +78,9 @@ def load():
     L.pa_wait.restype = C.c_int
     L.pa_wait.argtypes = [vp]
     L.pa_shard_ranges.restype = C.c_int
-    L.pa_shard_ranges.argtypes = [vp, C.POINTER(PaBatch), C.c_int32, C.c_double, vp]
+    L.pa_shard_ranges.argtypes = [vp, C.POINTER(PaBatch), C.c_int32, C.c_double, vp, vp]
     L.pa_shard_ranges_for.restype = C.c_int
-    L.pa_shard_ranges_for.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(PaBatch), C.c_int32, C.c_double, vp]
+    L.pa_shard_ranges_for.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(PaBatch), C.c_int32, C.c_double, vp, vp]
     L.pa_fetch_pep_scores.restype = C.c_int64
     L.pa_fetch_pep_scores.argtypes = [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp]
     L.pa_calculate_ambiguity.restype = C.c_int

@@ -30,11 +30,37 @@ def _cname(dt):
 class PyAscore:
     """Drop-in for pyascore.PyAscore (see the reference docstring, Ascore.pyx:13-59)."""
 
+    _MOD_CAP = 64          # mods per PSM the persistent result arrays hold (grown on demand)
+
     def __init__(self, bin_size, n_top, mod_group, mod_mass, mz_error=.5, fragment_types="by", device=0):
+        import ctypes as C
+        from . import _lib
         self._scorer = Scorer(bin_size, n_top, mod_group, mod_mass, mz_error, fragment_types, device=device)
         self._batch = None
         self._res = None
         self._k = 0
+        # A single score() is a batch of one through pa_score_batch.  Everything about that batch that does not
+        # change from call to call -- the one-entry CSR index arrays, the result arrays, the two ctypes structs --
+        # is built once here, so that a call costs a few attribute stores before it enters the library.
+        self._C, self._lib = C, _lib
+        self._a = dict(spec_off=np.zeros(2, np.int64), psm_spec=np.zeros(1, np.int32), pep_off=np.zeros(2, np.int32),
+                       n_mod=np.zeros(1, np.int32), max_charge=np.zeros(1, np.int32), aux_off=np.zeros(2, np.int32),
+                       mod_off=np.zeros(2, np.int64))
+        self._no_aux = (np.zeros(1, np.uint32), np.zeros(1, np.float32))
+        self._pb = _lib.PaBatch()
+        self._pb.n_spec, self._pb.n_psm = 1, 1
+        for k, v in self._a.items():
+            setattr(self._pb, k, v.ctypes.data)
+        self._pr = _lib.PaResults()
+        self._alloc_results(self._MOD_CAP)
+
+    def _alloc_results(self, cap):
+        self._cap = cap
+        self._out = dict(best_sig=np.zeros(1, np.uint64), best_score=np.zeros(1, np.float32), n_iso=np.zeros(1, np.int64),
+                         n_sites=np.zeros(1, np.int32), ascores=np.zeros(cap, np.float32), alt_sites=np.zeros(cap, np.uint64),
+                         psm_status=np.zeros(1, np.int32))
+        for k, v in self._out.items():
+            setattr(self._pr, k, v.ctypes.data)
 
     def add_neutral_loss(self, group, mass):
         self._scorer.add_neutral_loss(group, mass)
@@ -54,21 +80,36 @@ class PyAscore:
             raise ValueError("mz_arr and int_arr differ in length")
         use_aux = aux_mod_pos is not None and aux_mod_mass is not None
         pep = np.frombuffer(peptide.encode("utf8"), np.uint8)
-        batch = dict(
-            spec_off=np.array([0, mz_arr.size], np.int64), mz=mz_arr, inten=int_arr,
-            psm_spec=np.zeros(1, np.int32), pep_off=np.array([0, pep.size], np.int32), pep=pep,
-            n_mod=np.array([n_of_mod], np.int32), max_charge=np.array([max_fragment_charge], np.int32),
-            aux_off=np.array([0, aux_mod_pos.size if use_aux else 0], np.int32),
-            aux_pos=aux_mod_pos if use_aux else np.zeros(0, np.uint32),
-            aux_mass=aux_mod_mass if use_aux else np.zeros(0, np.float32))
-        res = self._scorer.score_batch(batch, keep_isoforms=True)
-        status = int(res["psm_status"][0])
-        self._batch, self._res, self._k = batch, res, int(n_of_mod)
+        n_aux = int(aux_mod_pos.size) if use_aux else 0
+        if use_aux and aux_mod_mass.size < n_aux:
+            raise ValueError("aux_mod_mass is shorter than aux_mod_pos")
+        k = int(n_of_mod)
+        if k > self._cap:
+            self._alloc_results(max(k, 2 * self._cap))
+        a, pb = self._a, self._pb
+        a["spec_off"][1] = mz_arr.size
+        a["pep_off"][1] = pep.size
+        a["n_mod"][0] = k
+        a["max_charge"][0] = max_fragment_charge
+        a["aux_off"][1] = n_aux
+        a["mod_off"][1] = k
+        ap, am = (aux_mod_pos, aux_mod_mass) if n_aux else self._no_aux
+        pb.mz, pb.inten, pb.pep = mz_arr.ctypes.data, int_arr.ctypes.data, (pep.ctypes.data if pep.size else self._no_aux[0].ctypes.data)
+        pb.aux_pos, pb.aux_mass = ap.ctypes.data, am.ctypes.data
+        self._res = None
+        # the batch as the result properties see it (and what keeps the caller's arrays alive until the next call)
+        self._batch = dict(mz=mz_arr, inten=int_arr, pep=pep, aux_pos=aux_mod_pos if n_aux else np.zeros(0, np.uint32),
+                           aux_mass=aux_mod_mass[:n_aux] if n_aux else np.zeros(0, np.float32))
+        self._k = k
         self._pep = peptide
+        sc = self._scorer
+        rc = sc.L.pa_score_batch(sc.h, self._C.byref(pb), self._C.byref(self._pr), self._lib.PA_KEEP_ISOFORMS)
+        if rc != 0:
+            sc._raise(rc)
+        status = int(self._out["psm_status"][0])
         if status != 0:
-            from ._lib import PSM_STATUS
-            self._res = None
-            raise ValueError("pyascore_b200: cannot score %r: %s" % (peptide, PSM_STATUS.get(status, status)))
+            raise ValueError("pyascore_b200: cannot score %r: %s" % (peptide, self._lib.PSM_STATUS.get(status, status)))
+        self._res = self._out
 
     def _need(self):
         if self._res is None:

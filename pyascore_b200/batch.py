@@ -204,7 +204,7 @@ class Scorer:
         if rc != 0:
             self._raise(rc)
 
-    def shard_ranges(self, batch, world, peak_weight=55.):
+    def shard_ranges(self, batch, world, peak_weight=55., share=None):
         """-> [(p0, p1)] * world: contiguous PSM ranges of a host batch cut on spectrum boundaries and balanced by
         estimated cost (pa_shard_ranges)"""
         add_mod_off(batch)
@@ -213,7 +213,9 @@ class Scorer:
         for k in _IN_KEYS:
             setattr(pb, k, _ptr(batch.get(k)))
         cuts = np.zeros(world + 1, np.int64)
-        rc = self.L.pa_shard_ranges(self.h, C.byref(pb), int(world), float(peak_weight), cuts.ctypes.data)
+        sh = None if share is None else np.ascontiguousarray(share, np.float64)
+        rc = self.L.pa_shard_ranges(self.h, C.byref(pb), int(world), float(peak_weight),
+                                    None if sh is None else sh.ctypes.data, cuts.ctypes.data)
         if rc != 0:
             raise ValueError("pyascore_b200: cannot shard this batch (host arrays with non-decreasing psm_spec needed)")
         return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
@@ -308,6 +310,10 @@ class MultiScorer:
                         for d in self.devices]
         self.mod_group = mod_group
         self.last_ranges = None
+        # share of a batch's cost each GPU gets; starts equal and follows the rates measured on the calls so far (the
+        # GPUs of a box do not get the same host-link bandwidth when all of them copy at once)
+        self.share = np.ones(len(self.devices))
+        self.adapt = True
 
     def close(self):
         for sc in self.scorers:
@@ -325,7 +331,7 @@ class MultiScorer:
             self.last_ranges = [(0, int(batch["n_mod"].shape[0]))]
             return self.scorers[0].score_batch(batch, out=out, want=want)
         try:
-            self.last_ranges = ranges = self.scorers[0].shard_ranges(batch, n, peak_weight)
+            self.last_ranges = ranges = self.scorers[0].shard_ranges(batch, n, peak_weight, self.share)
         except ValueError:                  # PSMs not in spectrum order: cannot be cut on spectrum boundaries
             self.last_ranges = [(0, int(batch["n_mod"].shape[0]))]
             return self.scorers[0].score_batch(batch, out=out, want=want)
@@ -345,6 +351,13 @@ class MultiScorer:
                 err = err or e
         if err is not None:
             raise err
+        if self.adapt:
+            # rate of every GPU on this call (cost units per millisecond, cost = its share of the cut); the next cut
+            # follows a smoothed version of it
+            ms = np.array([max(sc.counters()["ms_total"], 1e-3) for sc in self.scorers])
+            if np.all(np.array([b - a for a, b in ranges]) > 0):
+                rate = self.share / self.share.sum() / ms
+                self.share = 0.5 * self.share / self.share.sum() + 0.5 * rate / rate.sum()
         return out
 
     def counters(self):

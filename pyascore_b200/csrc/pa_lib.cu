@@ -12,6 +12,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -137,12 +139,18 @@ struct pa_scorer {
     size_t ev_used = 0;
     int attr_set = 0;
     bool binner_only = false;
-    // pa_score_batch_async: one orchestration thread per call in flight (at most one per scorer)
+    // pa_score_batch_async: the scorer's own orchestration thread (started on first use, parked between calls: a
+    // fresh thread per call would pay thread creation and the CUDA runtime's per-thread set-up every time)
     std::thread worker;
-    bool busy = false;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool busy = false;                     // a call is in flight (set by the caller, cleared by pa_wait)
+    bool job_ready = false, job_done = false, quit = false;
     int async_rc = PA_OK;
     pa_batch async_in;
     pa_results async_out;
+    int64_t async_lo = 0, async_hi = 0;
+    uint32_t async_flags = 0;
 };
 
 // Blocks of `kernel` one SM keeps resident at this block size and dynamic shared memory: the
@@ -583,7 +591,12 @@ extern "C" int pa_add_neutral_loss(pa_scorer* s, const char* group, float mass) 
 
 extern "C" void pa_destroy(pa_scorer* s) {
     if (!s) return;
-    if (s->busy && s->worker.joinable()) s->worker.join();
+    if (s->worker.joinable()) {
+        if (s->busy) pa_wait(s);
+        { std::lock_guard<std::mutex> lk(s->mu); s->quit = true; }
+        s->cv.notify_all();
+        s->worker.join();
+    }
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) s->slot[i].release();
@@ -1312,25 +1325,44 @@ extern "C" int pa_score_batch_async(pa_scorer* s, const pa_batch* in, const pa_r
         for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(s->slot[i].st, ev, 0));
         CK(cudaEventDestroy(ev));
     }
-    s->async_in = *in; s->async_out = *out;
     if (psm_hi < 0) psm_hi = in->n_psm;
-    s->busy = true;
-    s->async_rc = PA_OK;
-    try {
-        s->worker = std::thread([s, psm_lo, psm_hi, flags]() {
-            s->async_rc = score_impl(s, &s->async_in, &s->async_out, psm_lo, psm_hi, flags);
-        });
-    } catch (...) {
-        s->busy = false;
-        return fail(s, PA_ERR_STATE, "could not start the orchestration thread");
+    if (!s->worker.joinable()) {
+        try {
+            s->worker = std::thread([s]() {
+                std::unique_lock<std::mutex> lk(s->mu);
+                for (;;) {
+                    s->cv.wait(lk, [s] { return s->job_ready || s->quit; });
+                    if (s->quit) return;
+                    s->job_ready = false;
+                    lk.unlock();
+                    const int rc = score_impl(s, &s->async_in, &s->async_out, s->async_lo, s->async_hi, s->async_flags);
+                    lk.lock();
+                    s->async_rc = rc;
+                    s->job_done = true;
+                    s->cv.notify_all();
+                }
+            });
+        } catch (...) {
+            return fail(s, PA_ERR_STATE, "could not start the orchestration thread");
+        }
     }
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->async_in = *in; s->async_out = *out;
+        s->async_lo = psm_lo; s->async_hi = psm_hi; s->async_flags = flags;
+        s->async_rc = PA_OK;
+        s->job_done = false; s->job_ready = true;
+        s->busy = true;
+    }
+    s->cv.notify_all();
     return PA_OK;
 }
 
 extern "C" int pa_wait(pa_scorer* s) {
     if (!s) return PA_ERR_ARG;
     if (!s->busy) return PA_OK;
-    if (s->worker.joinable()) s->worker.join();
+    std::unique_lock<std::mutex> lk(s->mu);
+    s->cv.wait(lk, [s] { return s->job_done; });
     s->busy = false;
     return s->async_rc;
 }
@@ -1415,10 +1447,14 @@ extern "C" int pa_calculate_ambiguity(pa_scorer* s, int64_t psm, uint64_t sig_a,
 // psm_spec changes (one spectrum is binned by exactly one GPU).  Ranges are balanced by estimated cost, not by
 // count: isoforms x fragments per isoform for the scoring kernels plus `peak_weight` x the spectrum's peaks (shared
 // between the hits of a spectrum) for binning and, with host inputs, the host -> device copy that dominates there.
-// The estimate is taken on a strided sample (<= 32768 PSMs), so the call costs about a millisecond.
+// The estimate is taken on a strided sample (<= 8192 PSMs), so the call costs a fraction of a millisecond.  `share`
+// (optional, one positive number per rank) gives rank r that fraction of the cost instead of 1 / world: the GPUs of a box
+// do not all get the same host-link bandwidth when every one of them copies at once.
 extern "C" int pa_shard_ranges_for(const char* mod_group_c, int32_t n_types_in, int32_t nvar_in, const pa_batch* in,
-                                   int32_t world, double peak_weight, int64_t* cuts) {
+                                   int32_t world, double peak_weight, const double* share, int64_t* cuts) {
     if (!mod_group_c || !in || !cuts || world < 1) return PA_ERR_ARG;
+    double share_sum = 0.;
+    if (share) for (int r = 0; r < world; r++) { if (!(share[r] > 0.)) return PA_ERR_ARG; share_sum += share[r]; }
     const std::string mod_group(mod_group_c);
     const int64_t n = in->n_psm;
     for (int r = 0; r <= world; r++) cuts[r] = (r == world) ? n : 0;
@@ -1430,7 +1466,7 @@ extern "C" int pa_shard_ranges_for(const char* mod_group_c, int32_t n_types_in, 
     const bool term_n = mod_group.find('n') != std::string::npos, term_c = mod_group.find('c') != std::string::npos;
     const int n_types = std::max<int>(1, n_types_in);
     const int nvar = std::max(1, nvar_in);
-    const int64_t stride = std::max<int64_t>(1, n / 32768);
+    const int64_t stride = std::max<int64_t>(1, n / 8192);
     const int64_t m = (n + stride - 1) / stride;
     std::vector<double> cum(m + 1, 0.);
     for (int64_t i = 0; i < m; i++) {
@@ -1451,8 +1487,10 @@ extern "C" int pa_shard_ranges_for(const char* mod_group_c, int32_t n_types_in, 
         const double peaks = (double)(in->spec_off[sp + 1] - in->spec_off[sp]);
         cum[i + 1] = cum[i] + iso * frag + peak_weight * peaks / hits + 64.;
     }
+    double share_acc = 0.;
     for (int r = 1; r < world; r++) {
-        const double target = cum[m] * r / world;
+        share_acc += share ? share[r - 1] : 0.;
+        const double target = share ? cum[m] * share_acc / share_sum : cum[m] * r / world;
         int64_t i = std::lower_bound(cum.begin(), cum.end(), target) - cum.begin();
         int64_t p = std::min<int64_t>(std::max<int64_t>(i, 0) * stride, n);
         p = std::max(p, cuts[r - 1]);
@@ -1462,9 +1500,10 @@ extern "C" int pa_shard_ranges_for(const char* mod_group_c, int32_t n_types_in, 
     return PA_OK;
 }
 
-extern "C" int pa_shard_ranges(const pa_scorer* s, const pa_batch* in, int32_t world, double peak_weight, int64_t* cuts) {
+extern "C" int pa_shard_ranges(const pa_scorer* s, const pa_batch* in, int32_t world, double peak_weight,
+                               const double* share, int64_t* cuts) {
     if (!s) return PA_ERR_ARG;
-    return pa_shard_ranges_for(s->mod_group.c_str(), (int32_t)s->frag_types.size(), s->cfg.nvar_cap, in, world, peak_weight, cuts);
+    return pa_shard_ranges_for(s->mod_group.c_str(), (int32_t)s->frag_types.size(), s->cfg.nvar_cap, in, world, peak_weight, share, cuts);
 }
 
 // cpp/ModifiedPeptide.cpp:184-193

@@ -99,7 +99,7 @@ def gather_results(parts, ranges, n_psm, mod_off):
     return out
 
 
-def shard_ranges_native(batch, world, mod_group="STY", n_types=2, nl_variants=1, peak_weight=55.):
+def shard_ranges_native(batch, world, mod_group="STY", n_types=2, nl_variants=1, peak_weight=55., share=None):
     """The library's own cutter (pa_shard_ranges_for: strided-sample cost estimate, ~1 ms per million PSMs) -- what
     `MultiScorer` uses; host arithmetic only, so it runs without a GPU."""
     import ctypes as C
@@ -112,8 +112,9 @@ def shard_ranges_native(batch, world, mod_group="STY", n_types=2, nl_variants=1,
     for k in _IN_KEYS:
         setattr(pb, k, _ptr(batch.get(k)))
     cuts = np.zeros(world + 1, np.int64)
+    sh = None if share is None else np.ascontiguousarray(share, np.float64)
     rc = L.pa_shard_ranges_for(mod_group.encode("utf8"), int(n_types), int(nl_variants), C.byref(pb), int(world),
-                               float(peak_weight), cuts.ctypes.data)
+                               float(peak_weight), None if sh is None else sh.ctypes.data, cuts.ctypes.data)
     if rc != 0:
         raise ValueError("cannot shard this batch (host arrays with non-decreasing psm_spec needed)")
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]

@@ -109,3 +109,28 @@ def test_binning_equals_reference_on_awkward_intensities(n_top, bin_size):
     for inten in cases:
         a, b = O.binned(mz, inten), R.binned(mz, inten)
         assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_reference_behaviour_for_n_top_above_10():
+    """What `n_top > 10` means in the reference, as the reason the B200 library pins n_top to 10 for scoring
+    (include/pyascore_b200.h, PA_N_TOP): the weight vector has ten entries (cpp/Ascore.cpp:15-19), so PepScores, the
+    isoform order, best_sequence and the alternative sites are those of n_top = 10 -- deeper ranks only add count /
+    score columns and can move the depth calculateAmbiguity picks (cpp/Ascore.cpp:165-175)."""
+    w = synth.WORKLOADS["lowres_phospho"]
+    batch = synth.make_batch("lowres_phospho", 120, seed=7, chunk_index=9)
+    kw10, kw12 = dict(w["scorer"]), dict(w["scorer"], n_top=12)
+    R10, R12 = cscorer.RefPyAscore(**kw10), cscorer.RefPyAscore(**kw12)
+    moved = 0
+    for i in range(batch["n_mod"].size):
+        a = synth.psm_view(batch, i)
+        R10.score(*a)
+        R12.score(*a)
+        s10, c10, f10, w10, t10 = R10.pep_score_tables()
+        s12, c12, f12, w12, t12 = R12.pep_score_tables()
+        assert c12.shape[1] == 12 and f12.shape[1] == 12
+        assert _same(s10, s12) and _same(w10, w12) and _same(t10, t12)            # same isoforms, order and PepScores
+        assert _same(c10, np.ascontiguousarray(c12[:, :10])) and _same(f10, np.ascontiguousarray(f12[:, :10]))
+        assert R10.best_sequence == R12.best_sequence
+        assert all(_same(x, y) for x, y in zip(R10.alt_sites, R12.alt_sites))
+        moved += int(not _same(R10.ascores, R12.ascores))
+    assert moved < batch["n_mod"].size                                             # only Ascores can differ, and rarely do
