@@ -734,7 +734,9 @@ def run_config(name, batch, n_dev, args, peak, peak_src, clocks, sm_count, torch
     policy = best[0]
     e2e_s, _, ctrs, ranges = best[1]
     h2d = sum(c["bytes_h2d"] for c in ctrs)
-    # ---- every shard resident on its GPU ----
+    # ---- every shard resident on its GPU: cut for kernel time alone (equal shares, peaks weighted as binning work) ----
+    e2e_ranges = ranges
+    ranges = ms.scorers[0].shard_ranges(batch, n_dev, peak_weight=4.) if n_dev > 1 else ranges
     shards = [shard.take_shard(batch, a, b) for a, b in ranges]
     for sb in shards:
         pb.add_mod_off(sb)
@@ -775,7 +777,8 @@ def run_config(name, batch, n_dev, args, peak, peak_src, clocks, sm_count, torch
                 "d2h_bytes_per_step": int(sum(c["bytes_d2h"] for c in ctrs)), "h2d_achieved_gbs": h2d / e2e_s / 1e9,
                 "timing": "wall clock around MultiScorer.score_batch (cut + every range), one process, pinned host arrays",
                 "pinned_pages": policy, "placements_tried": tried},
-        "shard_psms": [b - a for a, b in ranges], "shard_share": [float(x) for x in ms.share / ms.share.sum()],
+        "shard_psms_resident": [b - a for a, b in ranges], "shard_psms_e2e": [b - a for a, b in e2e_ranges],
+        "shard_share_e2e": [float(x) for x in ms.share / ms.share.sum()],
         "shard_ms_cuda_events": [c["ms_total"] for c in ctrs],
         "kernel_ms_per_step_gpu0": kernel_ms(ctr0),
         "roofline_gpu0": roofline_of(name, shards[0], int(shards[0]["mod_off"][-1]), ctr0, peak, peak_src, clocks, sm_count),

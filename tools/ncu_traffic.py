@@ -17,8 +17,8 @@ for r in body:
     tot = 0.
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[ix[m]].replace(",", "")) * scale[units[ix[m]]]
-    key = {"k_bin_topn": "bin_topn", "k_select": "select", "k_select_thread": "select"}.get(name, "count_score" if name.startswith("k_count_score") else
-                                                             "ascore" if name.startswith("k_ascore") else name)
+    key = ("bin_topn" if name.startswith("k_bin_topn") else "select" if name.startswith("k_select") else
+           "count_score" if name.startswith("k_count_score") else "ascore" if name.startswith("k_ascore") else name)
     e = out.setdefault(key, {"dram_bytes_per_psm": 0., "warp_inst_per_psm": 0., "kernels": []})
     e["dram_bytes_per_psm"] += tot / n
     e["warp_inst_per_psm"] += float(r[ix["smsp__inst_executed.sum"]].replace(",", "")) / n
