@@ -39,14 +39,14 @@ class PaCounters(C.Structure):
                                          "n_fragment_lookups", "bytes_h2d", "bytes_d2h", "kernel_launches")] + \
                [(n, C.c_float) for n in ("ms_bin", "ms_plan", "ms_count", "ms_select", "ms_total")] + \
                [(n, C.c_int64) for n in ("launches_bin", "launches_count", "launches_select", "launches_ascore")] + \
-               [(n, C.c_float) for n in ("ms_ascore", "reserved")] + [("n_chunks", C.c_int64)]
+               [(n, C.c_float) for n in ("ms_ascore", "reserved")] + [("n_chunks", C.c_int64), ("n_spec_exact", C.c_int64)]
 
 
 EXPORTS = ["pa_create", "pa_add_neutral_loss", "pa_destroy", "pa_last_error", "pa_score_batch",
            "pa_fetch_pep_scores", "pa_calculate_ambiguity", "pa_format_sequence", "pa_site_positions",
            "pa_bin_spectra", "pa_tail_table", "pa_counters", "pa_alloc_pinned", "pa_free_pinned", "pa_version",
            "pa_create_binner", "pa_bin_spectra_ex", "pa_fragment_table", "pa_site_determining_ions", "pa_log_math",
-           "pa_power_set_sums", "pa_score_range", "pa_score_batch_async", "pa_wait", "pa_shard_ranges", "pa_shard_ranges_for", "pa_alloc_pinned_ex"]
+           "pa_power_set_sums", "pa_score_range", "pa_score_batch_async", "pa_wait", "pa_shard_ranges", "pa_shard_ranges_for", "pa_alloc_pinned_ex", "pa_narrow_mz"]
 
 _lib = None
 
@@ -99,6 +99,8 @@ def load():
     L.pa_alloc_pinned.argtypes = [C.c_int64]
     L.pa_alloc_pinned_ex.restype = vp
     L.pa_alloc_pinned_ex.argtypes = [C.c_int64, C.c_uint32]
+    L.pa_narrow_mz.restype = C.c_int64
+    L.pa_narrow_mz.argtypes = [vp, vp, C.c_int64, C.c_float, vp, vp]
     L.pa_free_pinned.restype = None
     L.pa_free_pinned.argtypes = [vp]
     L.pa_version.restype = C.c_int

@@ -12,8 +12,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "libpyascore_b200.so")
-SRCS = ["pa_lib.cu"]
-DEPS = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh"))) + ["../../include/pyascore_b200.h"]
+SRCS = ["pa_lib.cu", "pa_host.cpp"]
+DEPS = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".cpp"))) + ["../../include/pyascore_b200.h"]
 
 
 def needs_build():

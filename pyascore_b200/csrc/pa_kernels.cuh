@@ -69,6 +69,9 @@ struct PaBinArgs {
     const double* mz;
     const double* inten;     // intensities as float64 (the reference's dtype), or
     const float* inten32;    //   as float32 when the caller holds them in that precision (F32 instantiation)
+    const float* mz32;       // optional (then mz is not read): m/z narrowed to float32 by the host for the spectra it proved
+    const int32_t* esc_off;  //   safe (same bounds, same bin of every peak); per spectrum the offset of its exact float64
+    const double* mz_esc;    //   copy in mz_esc, or -1
     int64_t peak_base;       // spec_off values are relative to this
     int64_t n_spec;
     float2* rpk;             // retained peaks {(float)mz, rank as int bits}, m/z ascending, at the input offsets
@@ -140,11 +143,17 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
         if (P <= 0) { if (lane == 0) { a.rcount[s] = 0; a.chead[s] = make_float2(0.f, 0.f); } continue; }
         const bool fits = P <= cap;
         double mn, mx;
+        // m/z of peak i: float64 as given; or, when the host narrowed the batch (pa_narrow_mz), the float32 value widened
+        // again -- proven on the host to give the same bounds and bins -- unless this spectrum kept an exact copy
+        const double* em = a.mz;
+        if (a.mz32 != nullptr) em = (a.esc_off[s] >= 0) ? a.mz_esc + a.esc_off[s] - off : nullptr;
+        auto MZ = [&](int i) -> double { return em ? em[off + i] : (double)a.mz32[off + i]; };
         if (fits) {
             // stage the whole spectrum with asynchronous 8-byte copies: every load of the warp is
             // in flight at once (the arrays are only 8-byte aligned at a CSR offset)
             for (int i = lane; i < P; i += 32) {
-                pa_cp_async8(&s_mz[i], a.mz + off + i);
+                if (em) pa_cp_async8(&s_mz[i], em + off + i);
+                else s_mz[i] = (double)a.mz32[off + i];
                 if (F32) pa_cp_async4(&s_hi[i], a.inten32 + off + i);      // (lands where the ranking key of peak i will live)
                 else pa_cp_async8(&s_key[i], a.inten + off + i);
             }
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             // general path through global scratch (unsorted or oversized spectra)
             mn = INF; mx = -INF;
             for (int i = lane; i < P; i += 32) {
-                const double m = a.mz[off + i];
+                const double m = MZ(i);
                 mn = m < mn ? m : mn;
                 mx = m > mx ? m : mx;
             }
@@ -400,7 +409,7 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
             }
             bounds();
             for (int i = lane; i < P; i += 32) {
-                double q = floor(__ddiv_rn(__dsub_rn(a.mz[off + i], dmin), dbs));
+                double q = floor(__ddiv_rn(__dsub_rn(MZ(i), dmin), dbs));
                 long long bq = (long long)q;
                 if (bq > n_bins - 1) bq = n_bins - 1;
                 a.g_bin[off + i] = (int32_t)bq;
@@ -423,11 +432,11 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
                 int i = base + lane;
                 bool keep = (i < P) && a.g_tmp[off + i] != 255;
                 if (keep) {
-                    const float fi = __double2float_rn(a.mz[off + i]);
+                    const float fi = __double2float_rn(MZ(i));
                     int pos = 0;
                     for (int j = 0; j < P; j++) {
                         if (a.g_tmp[off + j] == 255 || j == i) continue;
-                        float fj = __double2float_rn(a.mz[off + j]);
+                        float fj = __double2float_rn(MZ(j));
                         pos += (fj < fi) || (fj == fi && j < i);
                     }
                     a.rpk[off + pos] = make_float2(fi, __int_as_float((int)a.g_tmp[off + i]));

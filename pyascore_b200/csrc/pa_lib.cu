@@ -6,6 +6,7 @@
 // the read-back of the plan totals (number of isoforms / work units), which sizes the scratch.
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cmath>
@@ -13,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -78,7 +80,7 @@ struct Slot {                // per-stream working set
     unsigned long long* h_lookups = nullptr;
     // small host batches (a single PyAscore.score call): every input array packed into one pinned block and copied
     // with one transfer, every result array read back with one; the user's (pageable) arrays are touched by memcpy only
-    DevBuf d_pack, d_opack;
+    DevBuf d_pack, d_opack, mz32, esc, escoff;
     unsigned char* h_pack = nullptr; size_t h_pack_cap = 0;
     unsigned char* h_opack = nullptr; size_t h_opack_cap = 0;
     cudaEvent_t ev_plan = nullptr;
@@ -86,7 +88,7 @@ struct Slot {                // per-stream working set
         DevBuf* all[] = {&spec_off, &mz, &inten, &inten32, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rpk, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lr, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &item_cnt, &item_off, &gen_flag, &asc_cursor, &d_pack, &d_opack, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lr, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &item_cnt, &item_off, &gen_flag, &asc_cursor, &d_pack, &d_opack, &mz32, &esc, &escoff, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_pack) cudaFreeHost(h_pack);
@@ -114,6 +116,91 @@ struct ChunkView {           // device-side views of the chunk in flight (kept f
 
 }  // namespace
 
+// ---- host-side narrowing of the m/z array -----------------------------------------------------------------
+// The end-to-end rate of a host batch is the host link's: 16 bytes per peak at ~53 GB/s.  What the kernels need from
+// the float64 m/z is little -- the spectrum's bounds (cpp/Spectra.cpp:46-48), the bin of every peak (:58-60) and
+// (float)m/z (Ascore.pyx:146) -- so the host may send the float32 value instead whenever it can PROVE that the value
+// widened back to double gives the same bounds and the same bins; (float)m/z is then the float32 itself.  The proof
+// per spectrum: the two bounds formulas evaluated on the rounded extremes, and for every peak the position of
+// (m/z - min) / bin_size between two integers -- further from both than float32 rounding can move it (one multiply,
+// vectorised), or else the reference's own formula evaluated on both values.  A spectrum that fails keeps an exact
+// float64 copy (a few per thousand on continuous data).  Runs on a small pool of host threads owned by the scorer while
+// the previous chunk's bytes are on the wire; the narrowed bytes are what the timed end-to-end region then moves.
+struct HostPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::function<void(int)> fn;
+    int n_tasks = 0, next = 0, left = 0;
+    uint64_t gen = 0;
+    bool quit = false;
+    void start(int n) {
+        for (int i = 0; i < n; i++)
+            th.emplace_back([this]() {
+                uint64_t seen = 0;
+                std::unique_lock<std::mutex> lk(mu);
+                for (;;) {
+                    cv_job.wait(lk, [&] { return quit || (gen != seen && next < n_tasks); });
+                    if (quit) return;
+                    while (next < n_tasks) {
+                        const int t = next++;
+                        lk.unlock();
+                        fn(t);
+                        lk.lock();
+                        if (--left == 0) cv_done.notify_all();
+                    }
+                    seen = gen;
+                }
+            });
+    }
+    void run_async(int tasks, std::function<void(int)> f) {    // the pool threads alone; wait() collects
+        std::lock_guard<std::mutex> lk(mu);
+        fn = std::move(f); n_tasks = tasks; next = 0; left = tasks; gen++;
+        cv_job.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return left == 0; });
+    }
+    void run(int tasks, std::function<void(int)> f) {          // the calling thread works too
+        std::unique_lock<std::mutex> lk(mu);
+        fn = std::move(f); n_tasks = tasks; next = 0; left = tasks; gen++;
+        cv_job.notify_all();
+        while (next < n_tasks) {
+            const int t = next++;
+            lk.unlock();
+            fn(t);
+            lk.lock();
+            --left;
+        }
+        cv_done.wait(lk, [&] { return left == 0; });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv_job.notify_all();
+        for (auto& t : th) if (t.joinable()) t.join();
+        th.clear();
+    }
+};
+
+struct NarrowStage {          // one of three rotating staging sets of the narrowing pass (chunk c uses set c % 3)
+    float* h_mz32 = nullptr; size_t h_mz32_cap = 0;        // pinned: narrowed m/z of the chunk,
+    double* h_esc = nullptr; size_t h_esc_cap = 0;         //   exact copies of the spectra that need them,
+    int32_t* h_escoff = nullptr; size_t h_escoff_cap = 0;  //   their per-spectrum offsets (-1: none)
+    std::vector<uint8_t> flags;
+    cudaEvent_t ev = nullptr;                              // the copies out of this set are done
+    bool busy = false;                                     // tasks in flight on the pool
+    int64_t s0 = 0, ns = 0, peak_lo = 0, npk = 0, n_esc = 0, n_flag = 0;
+    bool ok = false;
+    void release() {
+        if (h_mz32) cudaFreeHost(h_mz32);
+        if (h_esc) cudaFreeHost(h_esc);
+        if (h_escoff) cudaFreeHost(h_escoff);
+        if (ev) cudaEventDestroy(ev);
+        h_mz32 = nullptr; h_esc = nullptr; h_escoff = nullptr; ev = nullptr; h_mz32_cap = h_esc_cap = h_escoff_cap = 0;
+    }
+};
+
 struct pa_scorer {
     int device = 0;
     int sm_count = 148;
@@ -139,6 +226,10 @@ struct pa_scorer {
     size_t ev_used = 0;
     int attr_set = 0;
     bool binner_only = false;
+    HostPool pool;                         // host threads of the m/z narrowing pass (started on first use)
+    NarrowStage nstage[3];
+    int host_threads = 1;                  // PA_HOST_THREADS, default min(16, usable CPUs / GPUs of the box)
+    int narrow_mode = -1;                  // PA_NARROW: 0 never, 1 always, default: host chunks of >= 2^19 peaks
     // pa_score_batch_async: the scorer's own orchestration thread (started on first use, parked between calls: a
     // fresh thread per call would pay thread creation and the CUDA runtime's per-thread set-up every time)
     std::thread worker;
@@ -511,6 +602,14 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
     s = new pa_scorer();
     s->device = device;
     s->binner_only = binner_only;
+    {
+        int cpus = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+        s->host_threads = std::max(1, std::min(16, cpus / std::max(ndev, 1)));
+        if (const char* e = getenv("PA_HOST_THREADS")) s->host_threads = std::max(1, std::min(64, atoi(e)));
+        if (const char* e = getenv("PA_NARROW")) s->narrow_mode = (e[0] == '0') ? 0 : (e[0] == '1' ? 1 : -1);
+    }
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     s->mod_group = mod_group; s->frag_types = fragment_types;
     s->bin_size = bin_size; s->mod_mass = mod_mass; s->err = mz_error; s->n_top = n_top;
@@ -544,11 +643,13 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
             for (int z = 0; z < 16; z++) { volatile double zd = (double)z; zm[z] = zd * 1.007825; }
             CK(cudaMemcpyToSymbol(c_zmass, zm, sizeof(zm)));
         }
+        CK(cudaEventCreateWithFlags(&s->nstage[2].ev, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             CK(cudaStreamCreateWithFlags(&s->slot[i].st, cudaStreamNonBlocking));
             CK(cudaMallocHost(&s->slot[i].h_totals, sizeof(PlanTotals)));
             CK(cudaMallocHost(&s->slot[i].h_lookups, sizeof(unsigned long long)));
             CK(cudaEventCreateWithFlags(&s->slot[i].ev_plan, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->nstage[i].ev, cudaEventDisableTiming));
         }
         CK(cudaFuncSetAttribute(k_ascore_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_ascore_pairs<PA_MAXSTREAM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm)));
@@ -599,6 +700,8 @@ extern "C" void pa_destroy(pa_scorer* s) {
     }
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
+    s->pool.stop();
+    for (int i = 0; i < 3; i++) s->nstage[i].release();
     for (int i = 0; i < 2; i++) s->slot[i].release();
     s->d_T.release(); s->d_logd.release(); s->d_binom.release(); s->d_nl_sums.release(); s->d_nl_nvar.release();
     s->d_perm_pool.release(); s->d_perm_off.release(); s->d_lut.release();
@@ -652,6 +755,14 @@ static cudaError_t ensure_pinned(unsigned char*& p, size_t& cap, size_t bytes) {
     return e;
 }
 
+template <class T> static cudaError_t ensure_pinned_t(T*& p, size_t& cap, size_t count) {
+    unsigned char* q = (unsigned char*)p;
+    size_t bytes_cap = cap * sizeof(T);
+    cudaError_t e = ensure_pinned(q, bytes_cap, count * sizeof(T));
+    p = (T*)q; cap = bytes_cap / sizeof(T);
+    return e;
+}
+
 struct PackIn {                          // cursor over the packed input block (host image + device address)
     unsigned char* h; unsigned char* d; size_t used;
     template <class T> const T* add(const T* src, int64_t lo, int64_t n) {      // -> device view indexed with ABSOLUTE indices
@@ -666,6 +777,19 @@ struct PackIn {                          // cursor over the packed input block (
 struct PackOut {                         // one packed result array: where it sits in the block, where it goes on the host
     size_t off, bytes; void* dst;
 };
+
+// (pa_host.cpp: vectorised with the host compiler's AVX2 when the CPU has it)
+void pa_narrow_spectra(const double* mz, const int64_t* spec_off, int64_t sa, int64_t sb, int64_t peak_base,
+                       float bin_size, float* out32, uint8_t* flag);
+
+extern "C" int64_t pa_narrow_mz(const double* mz, const int64_t* spec_off, int64_t n_spec, float bin_size, float* out32,
+                                uint8_t* exact_flag) {
+    if (!mz || !spec_off || !out32 || !exact_flag || n_spec < 0 || !(bin_size > 0.f)) return PA_ERR_ARG;
+    pa_narrow_spectra(mz, spec_off, 0, n_spec, spec_off[0], bin_size, out32, exact_flag);
+    int64_t n = 0;
+    for (int64_t s = 0; s < n_spec; s++) n += exact_flag[s];
+    return n;
+}
 
 // ---- chunk boundaries of a device-resident batch --------------------------------------------------
 // Chunks a device-resident batch is cut into (the two streams alternate).  Measured on config 2 (1 M PSMs):
@@ -746,8 +870,58 @@ struct ChunkState {              // what the back half of a chunk needs from the
 
 struct ChunkEnds { int64_t peak_lo, peak_hi, pep_lo, pep_hi; };   // range ends of a device-resident chunk
 
+// Narrowing of the m/z of host chunk `r` into staging set `ns`: narrow_begin hands the per-spectrum work to the pool and
+// returns; narrow_end waits for it and lays out the exact copies.  The pipeline runs it one chunk ahead of the copies.
+static int narrow_begin(pa_scorer* s, NarrowStage& ns, const pa_batch* in, const ChunkRange& r) {
+    ns.ok = false; ns.busy = false;
+    ns.s0 = r.s0; ns.ns = r.s1 - r.s0;
+    ns.peak_lo = in->spec_off[r.s0]; ns.npk = in->spec_off[r.s1] - ns.peak_lo;
+    if (ns.ns <= 0 || !(s->narrow_mode == 1 || (s->narrow_mode < 0 && ns.npk >= (1 << 19) && s->host_threads >= 2))) return PA_OK;
+    CK(cudaEventSynchronize(ns.ev));                      // the chunk that used this set three chunks ago has left it
+    CK(ensure_pinned_t(ns.h_mz32, ns.h_mz32_cap, (size_t)ns.npk));
+    CK(ensure_pinned_t(ns.h_escoff, ns.h_escoff_cap, (size_t)ns.ns));
+    ns.flags.resize((size_t)ns.ns);
+    if (s->pool.th.empty()) s->pool.start(std::max(1, s->host_threads));
+    const int tasks = (int)std::min<int64_t>(ns.ns, (int64_t)s->host_threads * 4);
+    const double* mzh = in->mz; const int64_t* offh = in->spec_off;
+    float* o32 = ns.h_mz32; uint8_t* fl = ns.flags.data() - r.s0;
+    const float bsz = s->bin_size;
+    const int64_t s0 = r.s0, nsp = ns.ns, peak_lo = ns.peak_lo, npk = ns.npk;
+    s->pool.run_async(tasks, [=](int t) {
+        // tasks of about equal peak counts: cut the chunk's peak range evenly, snap to spectrum starts
+        const int64_t lo = peak_lo + npk * t / tasks, hi = peak_lo + npk * (t + 1) / tasks;
+        const int64_t sa = std::lower_bound(offh + s0, offh + s0 + nsp, lo) - offh;
+        const int64_t sb = (t + 1 == tasks) ? s0 + nsp : std::lower_bound(offh + s0, offh + s0 + nsp, hi) - offh;
+        pa_narrow_spectra(mzh, offh, sa, sb, peak_lo, bsz, o32, fl);
+    });
+    ns.busy = true;
+    return PA_OK;
+}
+
+static int narrow_end(pa_scorer* s, NarrowStage& ns, const pa_batch* in) {
+    if (!ns.busy) return PA_OK;
+    s->pool.wait();
+    ns.busy = false;
+    ns.n_esc = 0; ns.n_flag = 0;
+    for (int64_t q = 0; q < ns.ns; q++)
+        if (ns.flags[q]) { ns.n_esc += in->spec_off[ns.s0 + q + 1] - in->spec_off[ns.s0 + q]; ns.n_flag++; }
+    if (ns.n_esc * 4 > ns.npk) return PA_OK;              // m/z that sit on bin boundaries wholesale: nothing to gain
+    CK(ensure_pinned_t(ns.h_esc, ns.h_esc_cap, (size_t)std::max<int64_t>(ns.n_esc, 1)));
+    int64_t eo = 0;
+    for (int64_t q = 0; q < ns.ns; q++) {
+        ns.h_escoff[q] = -1;
+        if (!ns.flags[q]) continue;
+        const int64_t o = in->spec_off[ns.s0 + q], P = in->spec_off[ns.s0 + q + 1] - o;
+        ns.h_escoff[q] = (int32_t)eo;
+        memcpy(ns.h_esc + eo, in->mz + o, (size_t)P * 8);
+        eo += P;
+    }
+    ns.ok = true;
+    return PA_OK;
+}
+
 static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, const ChunkRange& r, int64_t mod_lo,
-                       int64_t mod_hi, int max_peaks, ChunkState& cs, const ChunkEnds* ends_dev) {
+                       int64_t mod_hi, int max_peaks, ChunkState& cs, const ChunkEnds* ends_dev, NarrowStage* nst = nullptr) {
     Slot& sl = s->slot[si];
     cudaStream_t st = sl.st;
     const int64_t np = r.p1 - r.p0, ns = r.s1 - r.s0;
@@ -769,7 +943,8 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     const int64_t n_aux = aux_hi - aux_lo;
     const size_t pack_bytes = (size_t)(ns + 1) * 8 + (size_t)npk * (in->inten32 ? 12 : 16) + (size_t)np * 12 + (size_t)(np + 1) * 16 +
                               (size_t)(pep_hi - pep_lo) + (size_t)n_aux * 8 + 16 * 16;
-    cs.packed = !in_dev && cs.single_chunk && pack_bytes <= PA_PACK_MAX;
+    bool narrowed = false;
+    cs.packed = !in_dev && cs.single_chunk && pack_bytes <= PA_PACK_MAX && s->narrow_mode != 1;
     if (cs.packed) {
         CK(ensure_pinned(sl.h_pack, sl.h_pack_cap, pack_bytes));
         CK(sl.d_pack.ensure(pack_bytes));
@@ -790,7 +965,22 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
         *h2d += (int64_t)pk.used;
     } else {
     CK(stage_in(sl.spec_off, in->spec_off, in_dev, r.s0, ns + 1, st, &b.spec_off, h2d));
-    CK(stage_in(sl.mz, in->mz, in_dev, peak_lo, npk, st, &v_mz, h2d));
+    // host batches: the m/z array goes over the link as float32 wherever the host proved that nothing the kernels
+    // derive from it changes (narrow_begin / narrow_end below); spectra that failed the proof come with an exact copy
+    if (nst != nullptr && nst->ok) {
+        CK(sl.mz32.ensure((size_t)std::max<int64_t>(npk, 1) * 4));
+        CK(sl.escoff.ensure((size_t)ns * 4));
+        CK(sl.esc.ensure((size_t)std::max<int64_t>(nst->n_esc, 1) * 8));
+        CK(cudaMemcpyAsync(sl.mz32.p, nst->h_mz32, (size_t)npk * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sl.escoff.p, nst->h_escoff, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+        if (nst->n_esc > 0) CK(cudaMemcpyAsync(sl.esc.p, nst->h_esc, (size_t)nst->n_esc * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(nst->ev, st));
+        *h2d += npk * 4 + ns * 4 + nst->n_esc * 8;
+        s->ctr.n_spec_exact += nst->n_flag;
+        narrowed = true;
+        v_mz = nullptr;
+    }
+    if (!narrowed) CK(stage_in(sl.mz, in->mz, in_dev, peak_lo, npk, st, &v_mz, h2d));
     if (in->inten32) CK(stage_in(sl.inten32, in->inten32, in_dev, peak_lo, npk, st, &v_int32, h2d));
     else CK(stage_in(sl.inten, in->inten, in_dev, peak_lo, npk, st, &v_int, h2d));
     CK(stage_in(sl.psm_spec, in->psm_spec, in_dev, r.p0, np, st, &b.psm_spec, h2d));
@@ -821,6 +1011,8 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     PaBinArgs ba;
     ba.spec_off = b.spec_off + r.s0;          // kernel indexes spectra 0..ns-1
     ba.mz = v_mz; ba.inten = v_int; ba.inten32 = v_int32; ba.peak_base = 0; ba.n_spec = ns;
+    ba.mz32 = narrowed ? sl.mz32.as<float>() - peak_lo : nullptr;
+    ba.esc_off = narrowed ? sl.escoff.as<int32_t>() : nullptr; ba.mz_esc = narrowed ? sl.esc.as<double>() : nullptr;
     ba.rpk = sl.rpk.as<float2>() - peak_lo; ba.rmz = nullptr; ba.rrank = nullptr;
     ba.g_bin = sl.g_bin.as<int32_t>() - peak_lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - peak_lo;
     ba.rcount = sl.rcount.as<int32_t>();
@@ -1255,21 +1447,36 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
     std::vector<ChunkState> cs(chunks.size());
     s->ctr.n_chunks = (int64_t)chunks.size();
     cs[0].single_chunk = chunks.size() == 1;
-    rc = chunk_front(s, 0, in, in_dev, chunks[0], mod_lo[0], mod_hi[0], chunk_maxp[0], cs[0], in_dev ? &ends_dev[0] : nullptr);
-    if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
+    // The m/z narrowing of a host chunk (narrow_begin / narrow_end) runs on the pool one chunk AHEAD of the copies: the
+    // set of chunk c+2 is being filled while chunk c+1 is on the wire and this thread waits for chunk c's plan, so the
+    // copy engine never waits for a conversion.  Three staging sets rotate; a set is reused once its copies are done.
+    const bool may_narrow = !in_dev && !(chunks.size() == 1 && s->narrow_mode != 1 && in->spec_off[chunks[0].s1] - in->spec_off[chunks[0].s0] < (1 << 19));
+    auto nstage = [&](size_t c) -> NarrowStage& { return s->nstage[c % 3]; };
+    auto bail = [&](int code) { if (may_narrow) for (int i = 0; i < 3; i++) if (s->nstage[i].busy) { s->pool.wait(); s->nstage[i].busy = false; } cudaDeviceSynchronize(); return code; };
+    if (may_narrow) {
+        rc = narrow_begin(s, nstage(0), in, chunks[0]);
+        if (rc == PA_OK) rc = narrow_end(s, nstage(0), in);
+        if (rc != PA_OK) return bail(rc);
+    }
+    rc = chunk_front(s, 0, in, in_dev, chunks[0], mod_lo[0], mod_hi[0], chunk_maxp[0], cs[0], in_dev ? &ends_dev[0] : nullptr,
+                     may_narrow ? &nstage(0) : nullptr);
+    if (rc != PA_OK) return bail(rc);
+    if (may_narrow && chunks.size() > 1) { rc = narrow_begin(s, nstage(1), in, chunks[1]); if (rc != PA_OK) return bail(rc); }
     for (size_t c = 0; c < chunks.size(); c++) {
         if (c + 1 < chunks.size()) {
             if (check_chunks) {
                 const char* why = prepare_host_chunk(c + 1);
-                if (why) { cudaDeviceSynchronize(); return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why); }
+                if (why) { bail(0); return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why); }
             }
+            if (may_narrow) { rc = narrow_end(s, nstage(c + 1), in); if (rc != PA_OK) return bail(rc); }
             // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
             rc = chunk_front(s, (int)((c + 1) & 1), in, in_dev, chunks[c + 1], mod_lo[c + 1], mod_hi[c + 1],
-                             chunk_maxp[c + 1], cs[c + 1], in_dev ? &ends_dev[c + 1] : nullptr);
-            if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
+                             chunk_maxp[c + 1], cs[c + 1], in_dev ? &ends_dev[c + 1] : nullptr, may_narrow ? &nstage(c + 1) : nullptr);
+            if (rc != PA_OK) return bail(rc);
+            if (may_narrow && c + 2 < chunks.size()) { rc = narrow_begin(s, nstage(c + 2), in, chunks[c + 2]); if (rc != PA_OK) return bail(rc); }
         }
         rc = chunk_back(s, (int)(c & 1), out, out_dev, cs[c], keep);
-        if (rc != PA_OK) { cudaDeviceSynchronize(); return rc; }
+        if (rc != PA_OK) return bail(rc);
     }
     for (int i = 0; i < 2; i++)
         CK(cudaMemcpyAsync(s->slot[i].h_lookups, s->slot[i].lookups.p, 8, cudaMemcpyDeviceToHost, s->slot[i].st));
@@ -1575,6 +1782,7 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     for (int64_t q = 0; q < n_spec; q++) m = std::max<int64_t>(m, spec_off[q + 1] - spec_off[q]);
     PaBinArgs ba;
     ba.spec_off = v_off; ba.mz = v_mz; ba.inten = v_int; ba.inten32 = nullptr; ba.peak_base = 0; ba.n_spec = n_spec;
+    ba.mz32 = nullptr; ba.esc_off = nullptr; ba.mz_esc = nullptr;
     ba.rpk = sl.rpk.as<float2>() - lo; ba.rmz = sl.rmz.as<float>() - lo; ba.rrank = sl.rrank.as<uint8_t>() - lo;
     ba.g_bin = sl.g_bin.as<int32_t>() - lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - lo;
     ba.rcount = sl.rcount.as<int32_t>(); ba.bin_size = s->bin_size; ba.n_top = s->n_top;

@@ -220,3 +220,47 @@ def test_spectra_block_narrows_float32_intensities(tmp_path):
     assert c32.inten is None and c32.inten32.dtype == np.float32
     assert c64.inten32 is None and c64.inten.dtype == np.float64
     assert np.array_equal(c32.inten32.astype(np.float64), SpectraParser(p32, "mzML").to_csr(narrow_intensity=False).inten)
+
+
+@pytest.mark.parametrize("workload,n", WORKLOADS)
+def test_narrowed_mz_equals_exact(workload, n, monkeypatch):
+    """host batches whose m/z the library narrows to float32 on the host (pa_narrow_mz) give, bit for bit, the results
+    of the float64 path -- including spectra with peaks on and next to bin boundaries (they keep an exact copy), an
+    unsorted spectrum, and float32 intensities on top"""
+    from pyascore_b200 import Scorer
+    batch = synth.make_batch(workload, n, seed=55, chunk_index=6)
+    off = batch["spec_off"]
+    mz = batch["mz"]
+    for q, val in ((2, 700.), (5, np.nextafter(900., 0.)), (7, np.nextafter(500., 1000.))):
+        a, b = int(off[q]), int(off[q + 1])
+        seg = mz[a:b]
+        seg[np.argmin(np.abs(seg - val))] = val                       # a peak on / just below / just above a bin boundary
+        mz[a:b] = np.sort(seg)
+    a, b = int(off[9]), int(off[10])
+    perm = np.random.default_rng(0).permutation(b - a)
+    mz[a:b] = mz[a:b][perm]
+    batch["inten"][a:b] = batch["inten"][a:b][perm]
+    w = synth.WORKLOADS[workload]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PA_NARROW", mode)
+        s = Scorer(**w["scorer"])
+        for g, m in w["neutral_losses"]:
+            s.add_neutral_loss(g, m)
+        res[mode] = s.score_batch(dict(batch))
+        c = s.counters()
+        res[mode + "_bytes"], res[mode + "_exact"] = c["bytes_h2d"], c["n_spec_exact"]
+        if mode == "1":
+            b32 = {k: v for k, v in batch.items() if k != "inten"}
+            b32["inten32"] = batch["inten"].astype(np.float32)
+            r32 = s.score_batch(b32)
+            monkeypatch.setenv("PA_NARROW", "0")
+            s0 = Scorer(**w["scorer"])
+            for g, m in w["neutral_losses"]:
+                s0.add_neutral_loss(g, m)
+            assert _same(s0.score_batch(b32), r32)
+            s0.close()
+        s.close()
+    assert _same(res["0"], res["1"])
+    assert res["0_exact"] == 0 and 1 <= res["1_exact"] < 0.05 * (off.size - 1)
+    assert res["1_bytes"] < 0.8 * res["0_bytes"]
