@@ -88,6 +88,8 @@ struct PaBinArgs {
     float bin_size;
     int n_top;
     int cap;                 // peaks per warp slot in shared memory
+    int32_t* list;           // k_bin_rows: the spectra it declines go here (count in *list_n); k_bin_topn: when non-null,
+    unsigned int* list_n;    //   the spectra to process (those k_bin_rows declined) instead of 0..n_spec-1
 };
 
 #define PA_NBIN_SMEM 128     // bins whose [start,end) ranges are tabulated in shared memory
@@ -137,7 +139,9 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
     const int n_top = a.n_top;
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
 
-    for (int64_t s = gw; s < a.n_spec; s += nw) {
+    const int64_t n_items = a.list ? (int64_t)*a.list_n : a.n_spec;
+    for (int64_t item = gw; item < n_items; item += nw) {
+        const int64_t s = a.list ? (int64_t)a.list[item] : item;
         const int64_t off = a.spec_off[s] - a.peak_base;
         const int P = (int)(a.spec_off[s + 1] - a.spec_off[s]);
         if (P <= 0) { if (lane == 0) { a.rcount[s] = 0; a.chead[s] = make_float2(0.f, 0.f); } continue; }
@@ -453,6 +457,8 @@ __global__ void __launch_bounds__(256) k_bin_topn(PaBinArgs a) {
         __syncwarp();
     }
 }
+
+#include "pa_bin_rows.cuh"
 
 __global__ void k_max_peaks(const int64_t* spec_off, int64_t n_spec, int* out) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

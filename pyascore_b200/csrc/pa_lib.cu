@@ -80,7 +80,7 @@ struct Slot {                // per-stream working set
     unsigned long long* h_lookups = nullptr;
     // small host batches (a single PyAscore.score call): every input array packed into one pinned block and copied
     // with one transfer, every result array read back with one; the user's (pageable) arrays are touched by memcpy only
-    DevBuf d_pack, d_opack, mz32, esc, escoff;
+    DevBuf d_pack, d_opack, mz32, esc, escoff, bin_list, bin_list_n;
     unsigned char* h_pack = nullptr; size_t h_pack_cap = 0;
     unsigned char* h_opack = nullptr; size_t h_opack_cap = 0;
     cudaEvent_t ev_plan = nullptr;
@@ -88,7 +88,7 @@ struct Slot {                // per-stream working set
         DevBuf* all[] = {&spec_off, &mz, &inten, &inten32, &psm_spec, &pep_off, &pep, &n_mod, &max_charge, &aux_off, &aux_pos,
                          &aux_mass, &mod_off, &rpk, &rmz, &rrank, &rcount, &ctab, &chead, &g_bin, &g_tmp, &psm_S, &psm_status, &psm_I,
                          &psm_units, &iso_off, &unit_off, &unit_psm, &totals, &cub_tmp, &iso_lo, &iso_hi, &iso_n,
-                         &iso_w, &g_sort, &g_lr, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &item_cnt, &item_off, &gen_flag, &asc_cursor, &d_pack, &d_opack, &mz32, &esc, &escoff, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
+                         &iso_w, &g_sort, &g_lr, &g_lists, &lookups, &sched, &best_idx, &mod_psm, &tie, &generic_list, &generic_count, &work_key, &work_key2, &work_val, &work_sorted, &rest_list, &item_cnt, &item_off, &gen_flag, &asc_cursor, &d_pack, &d_opack, &mz32, &esc, &escoff, &bin_list, &bin_list_n, &o_sig, &o_score, &o_niso, &o_nsites, &o_asc, &o_alt,
                          &o_status};
         for (DevBuf* b : all) b->release();
         if (h_pack) cudaFreeHost(h_pack);
@@ -230,6 +230,7 @@ struct pa_scorer {
     NarrowStage nstage[3];
     int host_threads = 1;                  // PA_HOST_THREADS, default min(16, usable CPUs / GPUs of the box)
     int narrow_mode = -1;                  // PA_NARROW: 0 never, 1 always, default: host chunks of >= 2^19 peaks
+    bool bin_rows = true;                  // PA_K1=topn: k_bin_topn alone (the row form k_bin_rows off)
     // pa_score_batch_async: the scorer's own orchestration thread (started on first use, parked between calls: a
     // fresh thread per call would pay thread creation and the CUDA runtime's per-thread set-up every time)
     std::thread worker;
@@ -279,6 +280,25 @@ static void bin_launch_shape(int sm_count, int64_t max_peaks, int64_t n_spec, in
         if (res * wpb > best_warps) { best_warps = res * wpb; best_wpb = wpb; best_res = res; }
     }
     *cap_out = cap; *wpb_out = best_wpb; *smem_out = (size_t)best_wpb * PA_BIN_SLOT_BYTES(cap);
+    *blocks_out = (int)std::max<int64_t>(1, std::min<int64_t>((n_spec + best_wpb - 1) / best_wpb, (int64_t)sm_count * best_res));
+}
+
+// Launch shape of k_bin_rows: slots of up to PA_ROWS_MAXCAP peaks (larger spectra are declined to k_bin_topn)
+typedef void (*bin_rows_fn)(PaBinArgs);
+static bin_rows_fn bin_rows_kernel(bool f32, bool narrow) {
+    return f32 ? (narrow ? k_bin_rows<true, true> : k_bin_rows<true, false>) : (narrow ? k_bin_rows<false, true> : k_bin_rows<false, false>);
+}
+
+static void bin_rows_launch_shape(int sm_count, int64_t max_peaks, int64_t n_spec, bin_rows_fn fn, int* cap_out, int* wpb_out,
+                                  size_t* smem_out, int* blocks_out) {
+    const int cap = (int)std::min<int64_t>(((std::max<int64_t>(max_peaks, 64) + 31) / 32) * 32, PA_ROWS_MAXCAP);
+    int best_wpb = 1, best_warps = 0, best_res = 1;
+    for (int wpb = 8; wpb >= 1; wpb--) {
+        const size_t smem = (size_t)wpb * PA_ROWS_SLOT_BYTES(cap);
+        const int res = resident_blocks(fn, wpb * 32, smem);
+        if (res * wpb > best_warps) { best_warps = res * wpb; best_wpb = wpb; best_res = res; }
+    }
+    *cap_out = cap; *wpb_out = best_wpb; *smem_out = (size_t)best_wpb * PA_ROWS_SLOT_BYTES(cap);
     *blocks_out = (int)std::max<int64_t>(1, std::min<int64_t>((n_spec + best_wpb - 1) / best_wpb, (int64_t)sm_count * best_res));
 }
 
@@ -608,6 +628,7 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
         if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
         s->host_threads = std::max(1, std::min(16, cpus / std::max(ndev, 1)));
         if (const char* e = getenv("PA_HOST_THREADS")) s->host_threads = std::max(1, std::min(64, atoi(e)));
+        if (const char* e = getenv("PA_K1")) s->bin_rows = strcmp(e, "topn") != 0;
         if (const char* e = getenv("PA_NARROW")) s->narrow_mode = (e[0] == '0') ? 0 : (e[0] == '1' ? 1 : -1);
     }
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -655,6 +676,8 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
         CK(cudaFuncSetAttribute(k_ascore_pairs<PA_MAXSTREAM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AscSm)));
         CK(cudaFuncSetAttribute(k_bin_topn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_bin_topn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int v = 0; v < 4; v++)
+            CK(cudaFuncSetAttribute(bin_rows_kernel((v & 1) != 0, (v & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(k_tail_table, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(k_ambiguity, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         int r = refresh_config(s);
@@ -1026,6 +1049,23 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     ba.cap = cap;
     cs.e_bin0 = next_event(s); cs.e_bin1 = next_event(s); cs.e_plan1 = next_event(s);
     CK(cudaEventRecord(cs.e_bin0, st));
+    ba.list = nullptr; ba.list_n = nullptr;
+    if (ns > 0 && s->bin_rows && s->n_top <= 31) {
+        // the row form takes the spectra that are the rule and lists the rest, which k_bin_topn then takes from the list
+        CK(sl.bin_list.ensure((size_t)ns * sizeof(int32_t)));
+        CK(sl.bin_list_n.ensure(sizeof(unsigned int)));
+        CK(cudaMemsetAsync(sl.bin_list_n.p, 0, sizeof(unsigned int), st));
+        ba.list = sl.bin_list.as<int32_t>(); ba.list_n = sl.bin_list_n.as<unsigned int>();
+        int rcap, rwpb, rblocks;
+        size_t rsmem;
+        const bin_rows_fn fn = bin_rows_kernel(ba.inten32 != nullptr, ba.mz32 != nullptr);
+        bin_rows_launch_shape(s->sm_count, max_peaks, ns, fn, &rcap, &rwpb, &rsmem, &rblocks);
+        ba.cap = rcap;
+        fn<<<std::max(rblocks, 1), rwpb * 32, rsmem, st>>>(ba);
+        CK(cudaGetLastError());
+        s->ctr.kernel_launches++; s->ctr.launches_bin++;
+        ba.cap = cap;
+    }
     if (ns > 0) {
         if (ba.inten32) k_bin_topn<true><<<std::max(blocks, 1), wpb * 32, smem, st>>>(ba);
         else k_bin_topn<false><<<std::max(blocks, 1), wpb * 32, smem, st>>>(ba);
@@ -1787,6 +1827,7 @@ extern "C" int pa_bin_spectra_ex(pa_scorer* s, int64_t n_spec, const int64_t* sp
     ba.g_bin = sl.g_bin.as<int32_t>() - lo; ba.g_tmp = sl.g_tmp.as<uint8_t>() - lo;
     ba.rcount = sl.rcount.as<int32_t>(); ba.bin_size = s->bin_size; ba.n_top = s->n_top;
     ba.ctab = sl.ctab.as<uint8_t>(); ba.chead = sl.chead.as<float2>();
+    ba.list = nullptr; ba.list_n = nullptr;
     ba.rindex = extra ? d_index.as<int32_t>() - lo : nullptr;
     ba.rbin = extra ? d_bin.as<int32_t>() - lo : nullptr;
     ba.bounds = extra ? d_bounds.as<float>() : nullptr;

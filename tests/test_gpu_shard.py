@@ -264,3 +264,43 @@ def test_narrowed_mz_equals_exact(workload, n, monkeypatch):
     assert _same(res["0"], res["1"])
     assert res["0_exact"] == 0 and 1 <= res["1_exact"] < 0.05 * (off.size - 1)
     assert res["1_bytes"] < 0.8 * res["0_bytes"]
+
+
+@pytest.mark.parametrize("f32", [False, True])
+@pytest.mark.parametrize("workload,n", WORKLOADS)
+def test_row_form_binning_equals_topn_kernel(workload, n, f32, monkeypatch):
+    """K1 has two kernels: k_bin_rows takes the spectra that are the rule and lists the rest for k_bin_topn.  With the
+    row form switched off (PA_K1=topn) k_bin_topn does everything; both ways must agree bit for bit -- on spectra with
+    tied intensities inside a bin (exact re-ranking), an unsorted spectrum, NaN / negative / huge m/z, an empty spectrum's
+    neighbours and peaks on bin boundaries (spectra beyond the row form's slot: the 2000-peak stress goldens)"""
+    batch = synth.make_batch(workload, n, seed=77, chunk_index=3)
+    off, mz, inten = batch["spec_off"], batch["mz"], batch["inten"]
+    rng = np.random.default_rng(5)
+    seg = lambda q: slice(int(off[q]), int(off[q + 1]))
+    for q in (1, 4, 11):                                               # ties: whole runs of equal intensities
+        sl = seg(q)
+        inten[sl] = np.round(inten[sl], -1) + 10.
+    v = inten[seg(2)]
+    v[1::2] = v[0]                                                     # half the peaks share one intensity
+    sl = seg(6)
+    perm = rng.permutation(sl.stop - sl.start)
+    mz[sl], inten[sl] = mz[sl][perm], inten[sl][perm]                  # unsorted
+    mz[int(off[8]) + 3] = np.nan
+    mz[int(off[9])] = -5.
+    mz[int(off[14]) - 1] = 3.0e6                                       # ascending, but an absurd range
+    sl = seg(15)
+    mz[sl] = np.sort(np.where(rng.random(sl.stop - sl.start) < 0.2, np.round(mz[sl], -2), mz[sl]))   # peaks on bin boundaries
+    v = mz[seg(16)]
+    v[1::2] = v[::2][: v[1::2].size]                                   # pairs of equal m/z
+    if f32:
+        batch = {k: v for k, v in batch.items() if k != "inten"}
+        batch["inten32"] = inten.astype(np.float32)
+    res = {}
+    for mode in ("topn", "rows"):
+        monkeypatch.setenv("PA_K1", mode)
+        s = _scorer(workload)
+        res[mode] = s.score_batch(dict(batch))
+        res[mode + "_launches"] = s.counters()["launches_bin"]
+        s.close()
+    assert _same(res["topn"], res["rows"])
+    assert res["rows_launches"] == 2 * res["topn_launches"]

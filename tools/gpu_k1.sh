@@ -11,5 +11,5 @@ d=json.loads(open('gpurun_out/${TAG}_bench_$W.json').read().strip().splitlines()
 print('$W', 'value %.4g' % d['value'], {k: round(v,2) for k,v in d['kernel_ms_per_step'].items()}, d['host_and_device_paths_bit_identical'])"
 done
 PROF="python bench.py --psms 262144 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-configs"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_bin_topn' -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_k1 $PROF > gpurun_out/${TAG}_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${K1_KERNEL:-k_bin_rows} -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_k1 $PROF > gpurun_out/${TAG}_ncu.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu.log
