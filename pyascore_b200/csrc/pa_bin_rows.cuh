@@ -1,16 +1,18 @@
 // K1 "row form": BinnedSpectra for the spectra that are the rule -- m/z ascending, at most PA_ROWS_MAXCAP peaks, a sane
 // m/z range, n_top <= 31.  cpp/Spectra.cpp:43-68 (bounds + bin index), :24-41 (top n_top of every bin by intensity).
 //
-// One warp per spectrum, three passes of one peak per lane and 32 peaks per round, nothing staged: a round of the binning
+// One warp per spectrum, two passes of one peak per lane and 32 peaks per round, nothing staged.  A round of the binning
 // pass reads its 32 m/z and intensities straight from global memory (coalesced 8- or 4-byte loads, the next round's already
-// in flight), and leaves (float)m/z, the ranking key (float)intensity and the bin in shared memory; the ranking pass is the
-// all-pairs count inside the bin's contiguous run [start, end) (four keys per LDS.128); the output pass compacts the kept
-// peaks with one ballot per round.  Shared memory is addressed with 32-bit shared-window addresses through ld/st.shared
-// (the generic-pointer form recomputes the window base at every access), full rounds carry no bounds predicates (the last,
-// partial round is a second instantiation of the same body), and "key > mine" costs 1.5 instructions (pa_gt_bits).
+// in flight), and leaves (float)m/z, the ranking key (float)intensity and the bin in shared memory, plus every bin's
+// contiguous run [start, end).  A round of the ranking pass counts, for each of its peaks, the keys of the run that beat
+// it (four keys per LDS.128) and writes the kept peaks out at once: one ballot compacts them, and each notes its position
+// in the m/z cell index with a shared-memory minimum.  Shared memory is addressed with 32-bit shared-window addresses
+// through ld/st.shared (the generic-pointer form recomputes the window base at every access), full rounds carry no bounds
+// predicates (the last, partial round is a second instantiation of the same body), and "key > mine" costs 1.5
+// instructions (pa_gt_bits).
 //
 // Everything unusual is DECLINED, not handled: the spectrum's index goes to a list and k_bin_topn (its exact general
-// paths included) runs over that list afterwards.  Declined: more peaks than the slot holds, m/z not ascending as float64
+// paths included) runs over that list afterwards.  Declined: more peaks than the slot holds, bins or (float)m/z not ascending
 // (or NaN), ends outside [0, 1e6], more than PA_NBIN_SMEM bins, and -- in the instantiation for host-narrowed m/z -- the
 // spectra that kept an exact float64 copy.  Ties on the float keys are handled here, as in k_bin_topn: the bin's mask of
 // taken ranks exposes them and the bin is re-ranked on the exact keys from global memory.
@@ -18,9 +20,9 @@
 #include <type_traits>
 
 #define PA_ROWS_MAXCAP 512
-// per warp: key f32[cap + 4] | mzf f32[cap] | bin u8[cap] | cnt u8[cap] | range u32[132] | tie mask u32[128] | cell u8[256]
+// per warp: key f32[cap + 4] | mzf f32[cap] | bin u8[cap] | cnt u8[cap] | range u32[132] | tie mask u32[128] | cell u32[256]
 #define PA_ROWS_RANGE_BYTES ((PA_NBIN_SMEM + 4) * 4)
-#define PA_ROWS_SLOT_BYTES(cap) ((size_t)(cap) * 10 + 16 + PA_ROWS_RANGE_BYTES + PA_NBIN_SMEM * 4 + PA_NCELL)
+#define PA_ROWS_SLOT_BYTES(cap) ((size_t)(cap) * 10 + 16 + PA_ROWS_RANGE_BYTES + PA_NBIN_SMEM * 4 + PA_NCELL * 4)
 
 // Counting "key > mine" at 1.5 instructions per key: FSET.BF leaves the BITS of 1.0f (0x3f800000 = 127 << 23) or 0, and the
 // integer sum of n such words is n * 127 << 23 modulo 2^32, from which n < 512 comes back as ((sum >> 23) * 383) & 511
@@ -31,10 +33,10 @@ __device__ __forceinline__ int pa_gt_bits(float a, float b) {
     return __float_as_int(d);
 }
 #define PA_GT4(v, hi) (pa_gt_bits((v).x, hi) + pa_gt_bits((v).y, hi) + pa_gt_bits((v).z, hi) + pa_gt_bits((v).w, hi))
-// the same for the first / last group of a run: only the keys at positions r .. r + 3 that fall inside [0, n) count
-#define PA_GT4_IN(v, hi, r, n)                                                                          \
-    (((unsigned)(r) < (n) ? pa_gt_bits((v).x, hi) : 0) + ((unsigned)((r) + 1) < (n) ? pa_gt_bits((v).y, hi) : 0) + \
-     ((unsigned)((r) + 2) < (n) ? pa_gt_bits((v).z, hi) : 0) + ((unsigned)((r) + 3) < (n) ? pa_gt_bits((v).w, hi) : 0))
+// the same for the first / last group of a run: key j counts where bit (sh + j) of w is set
+#define PA_GT4_IF(v, hi, w, sh)                                                                                   \
+    ((((w) >> (sh)) & 1u ? pa_gt_bits((v).x, hi) : 0) + (((w) >> ((sh) + 1)) & 1u ? pa_gt_bits((v).y, hi) : 0) + \
+     (((w) >> ((sh) + 2)) & 1u ? pa_gt_bits((v).z, hi) : 0) + (((w) >> ((sh) + 3)) & 1u ? pa_gt_bits((v).w, hi) : 0))
 __device__ __forceinline__ int pa_gt_count(int sum) { return (int)((((unsigned)sum >> 23) * 383u) & 511u); }
 
 // shared memory through 32-bit shared-window addresses
@@ -58,6 +60,8 @@ __device__ __forceinline__ uint4 pa_lds128u(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void pa_atoms_min(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void pa_sts128(uint32_t a, uint32_t v) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ uint32_t pa_atoms_or(uint32_t a, uint32_t v) {
     uint32_t old;
     asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
@@ -73,12 +77,12 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int cap = a.cap;
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)wib * (uint32_t)PA_ROWS_SLOT_BYTES(cap);
-    const uint32_t S_KEY = sb;                                  // ranking keys; after the ranking pass the kept m/z
+    const uint32_t S_KEY = sb;                                  // ranking keys
     const uint32_t S_MZF = sb + (uint32_t)cap * 4 + 16;
     const uint32_t S_BIN = sb + (uint32_t)cap * 8 + 16;
     const uint32_t S_CNT = S_BIN + (uint32_t)cap;
-    const uint32_t S_RANGE = S_CNT + (uint32_t)cap;             // start | end << 16 of every bin's run; entry 128 is a dummy
-    const uint32_t S_BMASK = S_RANGE + PA_ROWS_RANGE_BYTES;     // per bin: ranks taken (bit r), bit 31 = tie seen
+    const uint32_t S_RANGE = S_CNT + (uint32_t)cap + 4;         // start | end << 16 of every bin's run (entry -1: a dummy), then its walk word
+    const uint32_t S_BMASK = S_RANGE - 4 + PA_ROWS_RANGE_BYTES; // per bin: ranks taken (bit r), bit 31 = tie seen
     const uint32_t S_CELL = S_BMASK + PA_NBIN_SMEM * 4;
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const int n_top = a.n_top;
@@ -98,10 +102,11 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
         const int P = (int)Pl;
         const mz_t* __restrict__ mzp = (NARROW ? (const mz_t*)a.mz32 : (const mz_t*)a.mz) + off;
         const in_t* __restrict__ inp = (F32 ? (const in_t*)a.inten32 : (const in_t*)a.inten) + off;
-        // one round's loads: m/z of the peak and of its predecessor (the order test), intensity
-        mz_t mA = 0, pA = 0, mB = 0, pB = 0;
-        in_t kA = 0, kB = 0;
-        if (lane < P) { mA = mzp[lane]; pA = mzp[lane > 0 ? lane - 1 : 0]; kA = inp[lane]; }
+        // the loads of the first two rounds (the binning pass keeps two rounds in flight ahead of the one it works on)
+        mz_t mA = 0, mB = 0, mC = 0;
+        in_t kA = 0, kB = 0, kC = 0;
+        if (lane < P) { mA = mzp[lane]; kA = inp[lane]; }
+        if (lane + 32 < P) { mB = mzp[lane + 32]; kB = inp[lane + 32]; }
         const double mn = (double)mzp[0], mx = (double)mzp[P - 1];
         if (!(mn >= 0. && mx <= 1e6)) { decline(); continue; }          // (NaN ends fail both)
         // cpp/Spectra.cpp:46-48: the 100 is a literal there, independent of bin_size
@@ -115,10 +120,13 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
         pa_sts128z(S_BMASK + 16 * lane);
 
         // ---- binning ----
+        // The pass relies on what it checks: bins and (float)m/z never decrease from one peak to the next (then every bin
+        // is one contiguous run and the output is in m/z order).
         bool sorted = true;
-        int carry_bin = PA_NBIN_SMEM;                 // "no bin yet": its end lands in the dummy entry
+        int carry_bin = -1;                           // "no bin yet": its end lands in the dummy entry before S_RANGE
+        float carry_mz = __int_as_float(0xff800000);
         int bq = 0;
-        auto row = [&](auto tail, int i, mz_t m, mz_t mp, in_t kin) {
+        auto row = [&](auto tail, int i, mz_t m, in_t kin) {
             constexpr bool TAIL = decltype(tail)::value;
             const bool valid = !TAIL || i < P;
             // floor((m - min) / bin_size) as the reference computes it; the reciprocal product decides unless it
@@ -129,92 +137,137 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
             const double fr = __dsub_rn(t, q);
             if (!(fr > 1e-9 && fr < 1. - 1e-9)) q = floor(__ddiv_rn(x, dbs));
             bq = min(max((int)q, 0), top_bin);                           // (the conversion saturates; NaN -> 0)
-            if (TAIL && !valid) bq = PA_NBIN_SMEM;
+            const float mzf = NARROW ? (float)m : __double2float_rn((double)m);
             if (valid) {
-                sorted = sorted && (m >= mp);                            // NaN fails
-                pa_stsf(S_MZF + 4 * i, NARROW ? (float)m : __double2float_rn((double)m));
+                pa_stsf(S_MZF + 4 * i, mzf);
                 pa_stsf(S_KEY + 4 * i, F32 ? (float)kin : __double2float_rn((double)kin));
                 pa_sts8(S_BIN + i, (uint32_t)bq);
             }
             int bprev = __shfl_up_sync(PA_FULL, bq, 1);
-            if (lane == 0) bprev = carry_bin;
-            if (valid && bq != bprev) {
-                pa_sts16(S_RANGE + 4 * bq, (uint32_t)i);
-                pa_sts16(S_RANGE + 4 * bprev + 2, (uint32_t)i);
+            float fprev = __shfl_up_sync(PA_FULL, mzf, 1);
+            if (lane == 0) { bprev = carry_bin; fprev = carry_mz; }
+            if (valid) {
+                sorted = sorted && (bq >= bprev) && (mzf >= fprev);      // NaN fails
+                if (bq != bprev) {
+                    pa_sts16(S_RANGE + 4 * bq, (uint32_t)i);
+                    pa_sts16(S_RANGE + 4 * bprev + 2, (uint32_t)i);
+                }
             }
             carry_bin = __shfl_sync(PA_FULL, bq, 31);
+            carry_mz = __shfl_sync(PA_FULL, mzf, 31);
         };
         for (int base = 0;;) {
-            // A holds round `base`; the loads of the next round go out before A is worked on
-            int i = base + lane, in = i + 32;
-            if (in < P) { mB = mzp[in]; pB = mzp[in - 1]; kB = inp[in]; }
-            if (base + 32 <= P) row(std::false_type(), i, mA, pA, kA); else row(std::true_type(), i, mA, pA, kA);
+            // A, B, C take turns holding round `base`; the loads of round base + 64 go out before it is worked on
+            int in = base + 64 + lane;
+            if (in < P) { mC = mzp[in]; kC = inp[in]; }
+            if (base + 32 <= P) row(std::false_type(), base + lane, mA, kA); else row(std::true_type(), base + lane, mA, kA);
             base += 32;
             if (base >= P) break;
-            i = base + lane; in = i + 32;
-            if (in < P) { mA = mzp[in]; pA = mzp[in - 1]; kA = inp[in]; }
-            if (base + 32 <= P) row(std::false_type(), i, mB, pB, kB); else row(std::true_type(), i, mB, pB, kB);
+            in = base + 64 + lane;
+            if (in < P) { mA = mzp[in]; kA = inp[in]; }
+            if (base + 32 <= P) row(std::false_type(), base + lane, mB, kB); else row(std::true_type(), base + lane, mB, kB);
+            base += 32;
+            if (base >= P) break;
+            in = base + 64 + lane;
+            if (in < P) { mB = mzp[in]; kB = inp[in]; }
+            if (base + 32 <= P) row(std::false_type(), base + lane, mC, kC); else row(std::true_type(), base + lane, mC, kC);
             base += 32;
             if (base >= P) break;
         }
         if (lane == ((P - 1) & 31)) pa_sts16(S_RANGE + 4 * bq + 2, (uint32_t)P);       // the last run ends with the spectrum
         if (!__all_sync(PA_FULL, sorted)) { decline(); __syncwarp(); continue; }
         __syncwarp();
+        // Every run's [start, end) becomes, in place, what a peak of the run needs to walk it in groups of four keys:
+        // low half = byte offset of the first group | which of its four keys belong to the run, high half = the same
+        // for the last group (no keys when the run sits inside one group: the walk then adds nothing twice).
+        for (int b = lane; b < n_bins; b += 32) {
+            const uint32_t rg = pa_lds32(S_RANGE + 4 * b);
+            const uint32_t b0 = rg & 0xffffu, bl = (rg >> 16) - 1u;          // first and last peak of the run
+            const uint32_t a0 = b0 & ~3u, al = bl & ~3u;
+            uint32_t mf = (0xfu << (b0 & 3u)) & 0xfu;
+            uint32_t ml = 0xfu >> (3u - (bl & 3u));
+            if (a0 == al) { mf &= ml; ml = 0u; }
+            pa_sts32(S_RANGE + 4 * b, (a0 << 2) | mf | (((al << 2) | ml) << 16));
+        }
+        __syncwarp();
 
-        // ---- ranking: peaks of the same bin that beat this one, counted on the float keys ----
-        // Two peaks of a bin with the same key get the same count: every kept peak marks its count in the bin's mask,
-        // and a mark found already set flags the bin for exact ranking.
-        for (int base = 0; base < P; base += 32) {
-            const int i = base + lane;
-            if (i < P) {
+        // ---- ranking + output ----
+        // Rank = peaks of the same bin that beat this one, counted on the float keys.  Two peaks of a bin with the same key
+        // get the same count: every kept peak marks its count in the bin's mask, and a mark found already set flags the
+        // bin for exact ranking.  The round's kept peaks go out at once -- {mz, rank} in m/z order, and their positions
+        // into the m/z cell index -- on the assumption that no bin gets flagged; a flagged bin (rare) repeats the output.
+        // The cell index (consumers: pa_match_rank) needs a base and a power-of-two cell width that put every kept peak
+        // in [0, PA_NCELL): the spectrum's own ends serve, so a peak's cell is known the moment the peak is kept.
+        const float cbase = NARROW ? (float)mzp[0] : __double2float_rn(mn);
+        const float cinv = pa_cell_inv(cbase, NARROW ? (float)mzp[P - 1] : __double2float_rn(mx));
+        pa_sts128(S_CELL + 32 * lane, 0x7fffffffu);
+        pa_sts128(S_CELL + 32 * lane + 16, 0x7fffffffu);
+        __syncwarp();
+        float2* __restrict__ rpk = a.rpk + off;
+        int out = 0;
+        auto emit = [&](int i, int cnt) {               // (every lane calls; cnt = 255: not kept)
+            const bool keep = cnt < n_top;
+            const unsigned bal = __ballot_sync(PA_FULL, keep);
+            if (keep) {
+                const int pos = out + __popc(bal & below);
+                const float mzf = pa_ldsf(S_MZF + 4 * i);
+                rpk[pos] = make_float2(mzf, __int_as_float(cnt));
+                pa_atoms_min(S_CELL + 4 * pa_cell(mzf, cbase, cinv), (uint32_t)pos);    // first kept peak of the cell
+            }
+            out += __popc(bal);
+        };
+        auto rank = [&](auto tail, int i) {
+            constexpr bool TAIL = decltype(tail)::value;
+            int c = 255;
+            if (!TAIL || i < P) {
                 const uint32_t bqi = pa_lds8(S_BIN + i);
                 const float hi = pa_ldsf(S_KEY + 4 * i);
-                const uint32_t rg = pa_lds32(S_RANGE + 4 * bqi);
-                const int b0 = (int)(rg & 0xffffu), b1 = (int)(rg >> 16);
-                const unsigned n = (unsigned)(b1 - b0);
-                const int a0 = b0 & ~3, al = (b1 - 1) & ~3;              // first peak of the first / last group of four
-                uint32_t ga = S_KEY + 4 * a0;
-                const uint32_t gend = S_KEY + 4 * al;
+                const uint32_t w = pa_lds32(S_RANGE + 4 * bqi);
+                uint32_t ga = S_KEY + (w & 0xfff0u);
+                const uint32_t gend = S_KEY + ((w >> 16) & 0xfff0u);
                 float4 v = pa_lds128f(ga);
-                int acc = PA_GT4_IN(v, hi, a0 - b0, n);
+                int acc = PA_GT4_IF(v, hi, w, 0);
 #pragma unroll 1
                 for (ga += 16; ga < gend; ga += 16) {
                     v = pa_lds128f(ga);
                     acc += PA_GT4(v, hi);
                 }
-                if (al > a0) {
-                    v = pa_lds128f(gend);
-                    acc += PA_GT4_IN(v, hi, al - b0, n);
-                }
-                int c = pa_gt_count(acc);
-                if (c < n_top) {
-                    const uint32_t bit = 1u << c;
-                    if (pa_atoms_or(S_BMASK + 4 * bqi, bit) & bit) pa_atoms_or(S_BMASK + 4 * bqi, 0x80000000u);
-                } else c = 255;
+                v = pa_lds128f(gend);
+                acc += PA_GT4_IF(v, hi, w, 16);
+                c = pa_gt_count(acc);
+                const uint32_t bit = c < n_top ? 1u << c : 0u;
+                if (pa_atoms_or(S_BMASK + 4 * bqi, bit) & bit) pa_atoms_or(S_BMASK + 4 * bqi, 0x80000000u);
+                c = c < n_top ? c : 255;
                 pa_sts8(S_CNT + i, (uint32_t)c);
             }
+            emit(i, c);
+        };
+        {
+            int base = 0;
+            for (; base + 32 <= P; base += 32) rank(std::false_type(), base + lane);
+            if (base < P) rank(std::true_type(), base + lane);
         }
         __syncwarp();
         const uint4 tm = pa_lds128u(S_BMASK + 16 * lane);
-        const bool ties = __any_sync(PA_FULL, ((tm.x | tm.y | tm.z | tm.w) >> 31) != 0u);
-
-        // ---- output: kept peaks in m/z order as {mz, rank}; their m/z also over the keys, for the cell index ----
-        float2* __restrict__ rpk = a.rpk + off;
-        int out = 0;
-        for (int base = 0; base < P; base += 32) {
-            const int i = base + lane;
-            int cnt = 255;
-            float mzf = 0.f;
-            if (i < P) {
-                cnt = (int)pa_lds8(S_CNT + i);
-                mzf = pa_ldsf(S_MZF + 4 * i);
-                if (ties) {
+        if (__any_sync(PA_FULL, ((tm.x | tm.y | tm.z | tm.w) >> 31) != 0u)) {
+            // some bin has two equal float keys: its ranks come from the full intensity keys (read back from global
+            // memory; an equal intensity wins only from an earlier index) and the output is redone
+            pa_sts128(S_CELL + 32 * lane, 0x7fffffffu);
+            pa_sts128(S_CELL + 32 * lane + 16, 0x7fffffffu);
+            __syncwarp();
+            out = 0;
+            for (int base = 0; base < P; base += 32) {
+                const int i = base + lane;
+                int cnt = 255;
+                if (i < P) {
+                    cnt = (int)pa_lds8(S_CNT + i);
                     const uint32_t bqi = pa_lds8(S_BIN + i);
                     if (pa_lds32(S_BMASK + 4 * bqi) >> 31) {
-                        // exact rank from the full intensity keys (read back from global memory); an equal intensity
-                        // wins only from an earlier index
-                        const uint32_t rg = pa_lds32(S_RANGE + 4 * bqi);
-                        const int b0 = (int)(rg & 0xffffu), b1 = (int)(rg >> 16);
+                        const uint32_t w = pa_lds32(S_RANGE + 4 * bqi);                 // back to [b0, b1)
+                        const uint32_t mf = w & 0xfu, ml = (w >> 16) & 0xfu;
+                        const int b0 = (int)((w & 0xfff0u) >> 2) + (__ffs((int)mf) - 1);
+                        const int b1 = ml ? (int)(((w >> 16) & 0xfff0u) >> 2) + (32 - __clz((int)ml))
+                                          : (int)((w & 0xfff0u) >> 2) + (32 - __clz((int)mf));
                         const uint64_t ki = F32 ? (uint64_t)pa_inten_key32((float)inp[i]) : pa_inten_key((double)inp[i]);
                         int c = 0;
                         for (int j = b0; j < b1; j++) {
@@ -224,36 +277,16 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
                         cnt = c < n_top ? c : 255;
                     }
                 }
+                emit(i, cnt);
             }
-            const bool keep = cnt < n_top;
-            const unsigned bal = __ballot_sync(PA_FULL, keep);
-            if (keep) {
-                const int pos = out + __popc(bal & below);
-                rpk[pos] = make_float2(mzf, __int_as_float(cnt));
-                pa_stsf(S_KEY + 4 * pos, mzf);                          // (the keys are not read again)
-            }
-            out += __popc(bal);
+            __syncwarp();
         }
         if (lane == 0) a.rcount[s] = out;
-        // m/z cell index over the retained peaks (consumers: pa_match_rank), as k_bin_topn builds it
         if (out <= PA_RCAP && out > 0) {
-            __syncwarp();
-            const float cbase = pa_ldsf(S_KEY);
-            const float cinv = pa_cell_inv(cbase, pa_ldsf(S_KEY + 4 * (out - 1)));
-            pa_sts64(S_CELL + 8 * lane, 0x0101010101010101ull * (unsigned long long)out);
-            __syncwarp();
-            // cell[c] = first retained peak whose cell is >= c: mark the first peak of every occupied cell (empty =
-            // `out`), then take the suffix minimum over the 256 cells -- 8 cells per lane, a shuffle scan across lanes
-            for (int j = lane; j < out; j += 32) {
-                const int cj = pa_cell(pa_ldsf(S_KEY + 4 * j), cbase, cinv);
-                const int cp = j > 0 ? pa_cell(pa_ldsf(S_KEY + 4 * j - 4), cbase, cinv) : -1;
-                if (cj != cp) pa_sts8(S_CELL + cj, (uint32_t)j);
-            }
-            __syncwarp();
-            unsigned long long v = pa_lds64(S_CELL + 8 * lane);
-            unsigned bb[8];
-#pragma unroll
-            for (int t = 0; t < 8; t++) bb[t] = (unsigned)(v >> (8 * t)) & 0xffu;
+            // cell[c] = first kept peak whose cell is >= c: the suffix minimum over the 256 cells (empty ones hold a
+            // large value) -- 8 cells per lane, a shuffle scan across lanes, `out` past the last occupied cell
+            const uint4 c0 = pa_lds128u(S_CELL + 32 * lane), c1 = pa_lds128u(S_CELL + 32 * lane + 16);
+            unsigned bb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
             for (int t = 6; t >= 0; t--) bb[t] = min(bb[t], bb[t + 1]);
             unsigned x = bb[0];                      // suffix minimum over this and the higher lanes
@@ -263,7 +296,8 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
             }
             unsigned carry = __shfl_down_sync(PA_FULL, x, 1);
             if (lane == 31) carry = (unsigned)out;
-            v = 0;
+            carry = min(carry, (unsigned)out);
+            unsigned long long v = 0;
 #pragma unroll
             for (int t = 0; t < 8; t++) v |= (unsigned long long)min(bb[t], carry) << (8 * t);
             ((unsigned long long*)(a.ctab + (size_t)s * PA_NCELL))[lane] = v;
