@@ -14,15 +14,15 @@
 // Everything unusual is DECLINED, not handled: the spectrum's index goes to a list and k_bin_topn (its exact general
 // paths included) runs over that list afterwards.  Declined: more peaks than the slot holds, bins or (float)m/z not ascending
 // (or NaN), ends outside [0, 1e6], more than PA_NBIN_SMEM bins, and -- in the instantiation for host-narrowed m/z -- the
-// spectra that kept an exact float64 copy.  Ties on the float keys are handled here, as in k_bin_topn: the bin's mask of
-// taken ranks exposes them and the bin is re-ranked on the exact keys from global memory.
+// spectra that kept an exact float64 copy -- and, found out only at the end, spectra in which two peaks of a bin share a
+// float ranking key (k_bin_topn re-ranks such bins on the exact keys).
 #pragma once
 #include <type_traits>
 
 #define PA_ROWS_MAXCAP 512
-// per warp: key f32[cap + 4] | mzf f32[cap] | bin u8[cap] | cnt u8[cap] | range u32[132] | tie mask u32[128] | cell u32[256]
+// per warp: key f32[cap + 4] | mzf f32[cap] | bin u8[cap] | range u32[132] | cell u32[256]
 #define PA_ROWS_RANGE_BYTES ((PA_NBIN_SMEM + 4) * 4)
-#define PA_ROWS_SLOT_BYTES(cap) ((size_t)(cap) * 10 + 16 + PA_ROWS_RANGE_BYTES + PA_NBIN_SMEM * 4 + PA_NCELL * 4)
+#define PA_ROWS_SLOT_BYTES(cap) ((size_t)(cap) * 9 + 16 + PA_ROWS_RANGE_BYTES + PA_NCELL * 4)
 
 // Counting "key > mine" at 1.5 instructions per key: FSET.BF leaves the BITS of 1.0f (0x3f800000 = 127 << 23) or 0, and the
 // integer sum of n such words is n * 127 << 23 modulo 2^32, from which n < 512 comes back as ((sum >> 23) * 383) & 511
@@ -62,11 +62,6 @@ __device__ __forceinline__ uint4 pa_lds128u(uint32_t a) {
 }
 __device__ __forceinline__ void pa_atoms_min(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void pa_sts128(uint32_t a, uint32_t v) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(v)); }
-__device__ __forceinline__ uint32_t pa_atoms_or(uint32_t a, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
-    return old;
-}
 
 // F32: float32 intensities (pa_batch.inten32).  NARROW: float32 m/z from the host's narrowing pass (pa_narrow_mz).
 template <bool F32, bool NARROW>
@@ -80,10 +75,8 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
     const uint32_t S_KEY = sb;                                  // ranking keys
     const uint32_t S_MZF = sb + (uint32_t)cap * 4 + 16;
     const uint32_t S_BIN = sb + (uint32_t)cap * 8 + 16;
-    const uint32_t S_CNT = S_BIN + (uint32_t)cap;
-    const uint32_t S_RANGE = S_CNT + (uint32_t)cap + 4;         // start | end << 16 of every bin's run (entry -1: a dummy), then its walk word
-    const uint32_t S_BMASK = S_RANGE - 4 + PA_ROWS_RANGE_BYTES; // per bin: ranks taken (bit r), bit 31 = tie seen
-    const uint32_t S_CELL = S_BMASK + PA_NBIN_SMEM * 4;
+    const uint32_t S_RANGE = S_BIN + (uint32_t)cap + 4;         // start | end << 16 of every bin's run (entry -1: a dummy), then its walk word
+    const uint32_t S_CELL = S_RANGE - 4 + PA_ROWS_RANGE_BYTES;
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     const int n_top = a.n_top;
     const unsigned below = (1u << lane) - 1u;
@@ -117,7 +110,9 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
         if (n_bins > PA_NBIN_SMEM) { decline(); continue; }
         const int top_bin = n_bins - 1;
         const double dmin = (double)min_mz;
-        pa_sts128z(S_BMASK + 16 * lane);
+        pa_sts128z(S_RANGE - 4 + 16 * lane);          // empty bins: start = end = 0
+        if (lane == 0) pa_sts128z(S_RANGE - 4 + 512);
+        __syncwarp();
 
         // ---- binning ----
         // The pass relies on what it checks: bins and (float)m/z never decrease from one peak to the next (then every bin
@@ -180,9 +175,12 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
         // Every run's [start, end) becomes, in place, what a peak of the run needs to walk it in groups of four keys:
         // low half = byte offset of the first group | which of its four keys belong to the run, high half = the same
         // for the last group (no keys when the run sits inside one group: the walk then adds nothing twice).
+        int want = 0;                                 // sum over the runs of 0 + 1 + ... + (n - 1): see below
         for (int b = lane; b < n_bins; b += 32) {
             const uint32_t rg = pa_lds32(S_RANGE + 4 * b);
             const uint32_t b0 = rg & 0xffffu, bl = (rg >> 16) - 1u;          // first and last peak of the run
+            const int n = (int)(rg >> 16) - (int)b0;
+            want += (n * (n - 1)) >> 1;
             const uint32_t a0 = b0 & ~3u, al = bl & ~3u;
             uint32_t mf = (0xfu << (b0 & 3u)) & 0xfu;
             uint32_t ml = 0xfu >> (3u - (bl & 3u));
@@ -192,10 +190,8 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
         __syncwarp();
 
         // ---- ranking + output ----
-        // Rank = peaks of the same bin that beat this one, counted on the float keys.  Two peaks of a bin with the same key
-        // get the same count: every kept peak marks its count in the bin's mask, and a mark found already set flags the
-        // bin for exact ranking.  The round's kept peaks go out at once -- {mz, rank} in m/z order, and their positions
-        // into the m/z cell index -- on the assumption that no bin gets flagged; a flagged bin (rare) repeats the output.
+        // Rank = peaks of the same bin that beat this one, counted on the float keys.  The round's kept peaks go out at
+        // once -- {mz, rank} in m/z order, and their positions into the m/z cell index.
         // The cell index (consumers: pa_match_rank) needs a base and a power-of-two cell width that put every kept peak
         // in [0, PA_NCELL): the spectrum's own ends serve, so a peak's cell is known the moment the peak is kept.
         const float cbase = NARROW ? (float)mzp[0] : __double2float_rn(mn);
@@ -216,6 +212,7 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
             }
             out += __popc(bal);
         };
+        int got = 0;
         auto rank = [&](auto tail, int i) {
             constexpr bool TAIL = decltype(tail)::value;
             int c = 255;
@@ -235,10 +232,7 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
                 v = pa_lds128f(gend);
                 acc += PA_GT4_IF(v, hi, w, 16);
                 c = pa_gt_count(acc);
-                const uint32_t bit = c < n_top ? 1u << c : 0u;
-                if (pa_atoms_or(S_BMASK + 4 * bqi, bit) & bit) pa_atoms_or(S_BMASK + 4 * bqi, 0x80000000u);
-                c = c < n_top ? c : 255;
-                pa_sts8(S_CNT + i, (uint32_t)c);
+                got += c;
             }
             emit(i, c);
         };
@@ -247,40 +241,13 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
             for (; base + 32 <= P; base += 32) rank(std::false_type(), base + lane);
             if (base < P) rank(std::true_type(), base + lane);
         }
+        // Ties.  The count of a peak is its rank only if no other peak of its bin has the same float key (equal
+        // intensities, +-0, NaN).  Distinct keys give a bin of n peaks the counts 0 .. n-1 in some order; equal keys give
+        // some peak a smaller count and none a larger one.  So the counts of the whole spectrum add up to the sum of
+        // n (n - 1) / 2 over its bins exactly when no bin holds a tie -- one add per round and two warp reductions --
+        // and a spectrum that fails goes to k_bin_topn, which ranks on the exact keys and overwrites what was written here.
+        if (__reduce_add_sync(PA_FULL, got) != __reduce_add_sync(PA_FULL, want)) { decline(); __syncwarp(); continue; }
         __syncwarp();
-        const uint4 tm = pa_lds128u(S_BMASK + 16 * lane);
-        if (__any_sync(PA_FULL, ((tm.x | tm.y | tm.z | tm.w) >> 31) != 0u)) {
-            // some bin has two equal float keys: its ranks come from the full intensity keys (read back from global
-            // memory; an equal intensity wins only from an earlier index) and the output is redone
-            pa_sts128(S_CELL + 32 * lane, 0x7fffffffu);
-            pa_sts128(S_CELL + 32 * lane + 16, 0x7fffffffu);
-            __syncwarp();
-            out = 0;
-            for (int base = 0; base < P; base += 32) {
-                const int i = base + lane;
-                int cnt = 255;
-                if (i < P) {
-                    cnt = (int)pa_lds8(S_CNT + i);
-                    const uint32_t bqi = pa_lds8(S_BIN + i);
-                    if (pa_lds32(S_BMASK + 4 * bqi) >> 31) {
-                        const uint32_t w = pa_lds32(S_RANGE + 4 * bqi);                 // back to [b0, b1)
-                        const uint32_t mf = w & 0xfu, ml = (w >> 16) & 0xfu;
-                        const int b0 = (int)((w & 0xfff0u) >> 2) + (__ffs((int)mf) - 1);
-                        const int b1 = ml ? (int)(((w >> 16) & 0xfff0u) >> 2) + (32 - __clz((int)ml))
-                                          : (int)((w & 0xfff0u) >> 2) + (32 - __clz((int)mf));
-                        const uint64_t ki = F32 ? (uint64_t)pa_inten_key32((float)inp[i]) : pa_inten_key((double)inp[i]);
-                        int c = 0;
-                        for (int j = b0; j < b1; j++) {
-                            const uint64_t kj = F32 ? (uint64_t)pa_inten_key32((float)inp[j]) : pa_inten_key((double)inp[j]);
-                            c += (kj > ki) || (kj == ki && j < i);
-                        }
-                        cnt = c < n_top ? c : 255;
-                    }
-                }
-                emit(i, cnt);
-            }
-            __syncwarp();
-        }
         if (lane == 0) a.rcount[s] = out;
         if (out <= PA_RCAP && out > 0) {
             // cell[c] = first kept peak whose cell is >= c: the suffix minimum over the 256 cells (empty ones hold a
