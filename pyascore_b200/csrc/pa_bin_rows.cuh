@@ -63,6 +63,8 @@ __device__ __forceinline__ uint4 pa_lds128u(uint32_t a) {
 __device__ __forceinline__ void pa_atoms_min(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void pa_sts128(uint32_t a, uint32_t v) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(v)); }
 
+__device__ __forceinline__ void pa_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // F32: float32 intensities (pa_batch.inten32).  NARROW: float32 m/z from the host's narrowing pass (pa_narrow_mz).
 template <bool F32, bool NARROW>
 __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
@@ -87,7 +89,19 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
     if (gw < a.n_spec) { o0 = a.spec_off[gw]; o1 = a.spec_off[gw + 1]; }
     for (int64_t s = gw; s < a.n_spec; s += nw) {
         const int64_t off = o0 - a.peak_base, Pl = o1 - o0;
-        if (s + nw < a.n_spec) { o0 = a.spec_off[s + nw]; o1 = a.spec_off[s + nw + 1]; }     // the next spectrum's, early
+        if (s + nw < a.n_spec) {
+            // the next spectrum's offsets, early -- and its peaks on their way into L2: one prefetch per 128-byte line, the
+            // warp covers a whole array with one instruction, so that the loads of the binning pass find them there
+            o0 = a.spec_off[s + nw]; o1 = a.spec_off[s + nw + 1];
+            const int64_t pn = o1 - o0;
+            if (pn > 0) {
+                const char* pm = (const char*)((NARROW ? (const mz_t*)a.mz32 : (const mz_t*)a.mz) + (o0 - a.peak_base));
+                const char* pi = (const char*)((F32 ? (const in_t*)a.inten32 : (const in_t*)a.inten) + (o0 - a.peak_base));
+                const int64_t bm = pn * (int64_t)sizeof(mz_t), bi = pn * (int64_t)sizeof(in_t), at = (int64_t)lane * 128;
+                if (at < bm + 128) pa_prefetch_l2(pm + (at < bm ? at : bm - 1));
+                if (at < bi + 128) pa_prefetch_l2(pi + (at < bi ? at : bi - 1));
+            }
+        }
         if (Pl <= 0) { if (lane == 0) { a.rcount[s] = 0; a.chead[s] = make_float2(0.f, 0.f); } continue; }
         auto decline = [&]() { if (lane == 0) a.list[atomicAdd(a.list_n, 1u)] = (int32_t)s; };
         if (Pl > cap) { decline(); continue; }
