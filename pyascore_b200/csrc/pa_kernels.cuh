@@ -679,6 +679,107 @@ __device__ __forceinline__ void pa_walk_isoform(const PaCfg& cfg, const PsmSmem*
     }
 }
 
+// ---- the walk of the common case: staged peaks with a cell index, 2 <= L <= 64 ------------------------------
+// Same arithmetic as pa_walk_isoform / pa_emit_step / pa_match_rank, fewer instructions per step: the residue states of
+// the walk come off a 64-bit word one bit per step (reversed up front for the y-side walks) instead of a variable shift of
+// a 128-bit mask, the residue table is followed by a running shared-memory address, the peaks need no "are they staged"
+// test per lookup, and the increment table is read through a 32-bit shared address.
+struct PaFastCtx {
+    uint32_t res_a, nli_a, pk_a, cell_a, lut_a, nl_a;     // shared-window addresses: res[][2], nlidx[][2], pk[], cell[], lut[], s_nl
+    float cbase, cinv, err;
+    int Z, L;
+};
+
+__device__ __forceinline__ float pa_lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t pa_lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 pa_lds_f32x2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 pa_lds_u64x2(uint32_t a) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
+    return v;
+}
+
+// rank of the best retained peak matching fragment f (pa_match_rank, staged form), added into the packed counters
+template <bool EGH>
+__device__ __forceinline__ void pa_fast_lookup(const PaFastCtx& c, float f, int egh_rt, unsigned long long& clo,
+                                               unsigned long long& chi) {
+    const bool err_gt_half = EGH && egh_rt;
+    const float lo = __fsub_rn(f, c.err), hi = __fadd_rn(f, c.err);
+    int best = 10;                                   // lut[10] = no increment
+    uint32_t pa = c.pk_a + 8u * pa_lds_u8(c.cell_a + (uint32_t)pa_cell(lo, c.cbase, c.cinv));
+    float2 e = pa_lds_f32x2(pa), e_next = pa_lds_f32x2(pa + 8);
+    for (;;) {
+        if (!(e.x < hi)) break;
+        if (e.x > lo && !(err_gt_half && !((double)f >= (double)e.x - .5))) {
+            const int r = __float_as_int(e.y);
+            best = r < best ? r : best;
+        }
+        pa += 8;
+        e = e_next;
+        if (!(e.x < hi)) break;
+        e_next = pa_lds_f32x2(pa + 8);
+    }
+    const ulonglong2 inc = pa_lds_u64x2(c.lut_a + 16u * (uint32_t)best);
+    clo += inc.x; chi += inc.y;
+}
+
+template <bool HAS_NL, bool EGH>
+__device__ __forceinline__ void pa_walk_fast(const PaCfg& cfg, const PaFastCtx& c, uint64_t mlo, char type, int s0, int s1,
+                                             unsigned long long& clo, unsigned long long& chi, uint32_t& nfrag) {
+    clo = 0; chi = 0; nfrag = 0;
+    const bool fwd = (type == 'b' || type == 'c');
+    double a1, a2;
+    pa_type_consts(type, a1, a2);
+    const double zm1 = c_zmass[1], zm2 = c_zmass[2];
+    // bit t of `w` = state of the residue visited at step t
+    uint64_t w = fwd ? mlo : (__brevll(mlo) >> (64 - c.L));
+    uint32_t ra = fwd ? c.res_a : c.res_a + 8u * (uint32_t)(c.L - 1);
+    uint32_t na = fwd ? c.nli_a : c.nli_a + 2u * (uint32_t)(c.L - 1);
+    const int dr = fwd ? 8 : -8, dn = fwd ? 2 : -2;
+    float run = 0.f;
+    int nls = 0;
+    // replay of the running sum up to the lane's segment (the adds must stay sequential: the reference's rounding)
+    for (int step = 0; step < s0; step++) {
+        const uint32_t st = (uint32_t)w & 1u;
+        w >>= 1;
+        run = __fadd_rn(pa_lds_f32(ra + 4u * st), run);
+        if (HAS_NL) {
+            const int idx = (int)pa_lds_u8(na + st);
+            if (idx) nls = pa_nl_bump(nls, idx);
+            na += dn;
+        }
+        ra += dr;
+    }
+    const int Z = c.Z;
+    for (int step = s0; step < s1; step++) {
+        const uint32_t st = (uint32_t)w & 1u;
+        w >>= 1;
+        run = __fadd_rn(pa_lds_f32(ra + 4u * st), run);
+        ra += dr;
+        int nv = 1;
+        if (HAS_NL) {
+            const int idx = (int)pa_lds_u8(na + st);
+            if (idx) nls = pa_nl_bump(nls, idx);
+            na += dn;
+            nv = (int)pa_lds_u8(c.nl_a + 256 * 16 * 4 + (uint32_t)nls);
+        }
+        for (int v = 0; v < nv; v++) {
+            float base = run;
+            if (HAS_NL) base = __fsub_rn(run, pa_lds_f32(c.nl_a + 4u * (uint32_t)(nls * 16 + v)));
+            const double d = __dsub_rn(__dadd_rn((double)base, a1), a2);
+            // charge z: (d + z * 1.007825) / z  (cpp/ModifiedPeptide.cpp:585-587); 1 and 2 are unrolled
+            pa_fast_lookup<EGH>(c, __double2float_rn(__dadd_rn(d, zm1)), cfg.err_gt_half, clo, chi);
+            if (Z >= 2) pa_fast_lookup<EGH>(c, __double2float_rn(__dmul_rn(__dadd_rn(d, zm2), 0.5)), cfg.err_gt_half, clo, chi);
+            for (int z = 3; z <= Z; z++) pa_fast_lookup<EGH>(c, pa_charge_mz(d, z), cfg.err_gt_half, clo, chi);
+        }
+        nfrag += (uint32_t)(nv * Z);
+    }
+}
+
 // packed per-rank counts -> packed cumulative counts (cpp/Ascore.cpp:113-117)
 __device__ __forceinline__ void pa_cumulate(unsigned long long& lo, unsigned long long& hi) {
     // prefix sums of 12-bit fields; totals stay < 4096 (PA_MAX_FRAGMENTS)
@@ -738,6 +839,15 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
     const int64_t gw = (int64_t)blockIdx.x * wpb + wib, nw = (int64_t)gridDim.x * wpb;
     int64_t cur = -1;
     PsmInfo info;
+    PaFastCtx fc;
+    bool fast = false;
+    fc.res_a = (uint32_t)__cvta_generic_to_shared(&sm->res[0][0]);
+    fc.nli_a = (uint32_t)__cvta_generic_to_shared(&sm->nlidx[0][0]);
+    fc.pk_a = (uint32_t)__cvta_generic_to_shared(&sm->pk[0]);
+    fc.cell_a = (uint32_t)__cvta_generic_to_shared(&sm->cell[0]);
+    fc.lut_a = (uint32_t)__cvta_generic_to_shared(&s_lut[0]);
+    fc.nl_a = (uint32_t)__cvta_generic_to_shared(&s_nl[0]);
+    fc.err = cfg.err; fc.cbase = 0.f; fc.cinv = 0.f; fc.Z = 0; fc.L = 0;
     unsigned long long lookups = 0;
     const int T = PAIR ? 2 : 1;
     // Units differ in cost by two orders of magnitude (1 .. 1024 isoforms), so they are handed out
@@ -757,7 +867,13 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
       for (int64_t u = base; u < u_end; u++) {
         const int64_t p = a.unit_psm[u];
         const int64_t I = a.iso_off[p + 1] - a.iso_off[p];
-        if (p != cur) { pa_setup_psm(cfg, b, p, sm, info, true); cur = p; }
+        if (p != cur) {
+            pa_setup_psm(cfg, b, p, sm, info, true);
+            cur = p;
+            // the common case takes the leaner walk (pa_walk_fast): peaks staged with their cell index, 2 <= L <= 64
+            fast = info.cell != nullptr && info.L >= 2 && info.L <= 64;
+            fc.cbase = info.cell_base; fc.cinv = info.cell_inv; fc.Z = info.Z; fc.L = info.L;
+        }
         const int S = a.psm_S[p], k = info.k;
         const int64_t first = (int64_t)(u - a.unit_off[p]) * PA_UNIT;
         const int cnt = (int)((I - first < PA_UNIT) ? I - first : PA_UNIT);
@@ -777,7 +893,17 @@ __global__ void __launch_bounds__(256, PA_K2_MINBLOCKS) k_count_score(PaCfg cfg,
                 uint64_t mlo, mhi;
                 pa_sites_to_mask(sm, bits, mlo, mhi);
                 const int s0 = (steps * h) >> hs, s1 = (steps * (h + 1)) >> hs;
-                if (PAIR) {
+                if (fast) {
+                    if (PAIR) {
+                        pa_walk_fast<HAS_NL, EGH>(cfg, fc, mlo, cfg.types[sub >> hs], s0, s1, clo, chi, nf);
+                    } else {
+                        for (int t = 0; t < cfg.n_types; t++) {
+                            unsigned long long xlo, xhi; uint32_t xn;
+                            pa_walk_fast<HAS_NL, EGH>(cfg, fc, mlo, cfg.types[t], s0, s1, xlo, xhi, xn);
+                            clo += xlo; chi += xhi; nf += xn;
+                        }
+                    }
+                } else if (PAIR) {
                     pa_walk_isoform<HAS_NL, EGH>(cfg, sm, info, s_nl, mlo, mhi, cfg.types[sub >> hs], 0, 0.f, 0, s0, s1, s_lut, clo, chi, nf);
                 } else {
                     for (int t = 0; t < cfg.n_types; t++) {
