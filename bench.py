@@ -599,6 +599,11 @@ def main():
                     "h2d_concurrent_peak_gbs": pcie_together,
                     "h2d_copy_peak_write_combined_gbs": pcie_wc, "h2d_concurrent_peak_write_combined_gbs": pcie_together_wc,
                     "h2d_frac_of_ceiling": (h2d_ach / ceiling) if ceiling else None,
+                    "host_narrowing": {"spectra_kept_exact_per_step": int(ctr_e2e["n_spec_exact"]),
+                                       "ms_waited_per_step": float(ctr_e2e["ms_narrow_wait"]),
+                                       "what": "m/z of host batches goes over the link as float32 wherever the library's host pass "
+                                               "(pa_narrow_mz, inside the timed call) proves bounds and bins unchanged; "
+                                               "PA_NARROW=0 turns it off"},
                     "note": "bound by the host->device link: h2d_achieved_gbs (rank 0's bytes / the slowest rank's time) vs a "
                             "plain pinned 1 GiB copy alone (h2d_copy_peak_gbs) and with every rank copying at once "
                             "(h2d_concurrent_peak_gbs, per rank; the ceiling is the slowest)"},

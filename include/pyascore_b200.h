@@ -228,7 +228,8 @@ typedef struct {
     int64_t kernel_launches;           /* kernels launched by the last pa_score_batch */
     float ms_bin, ms_plan, ms_count, ms_select, ms_total; /* CUDA-event times, summed over chunks */
     int64_t launches_bin, launches_count, launches_select, launches_ascore;
-    float ms_ascore, reserved;          /* ms_select = best-isoform selection, ms_ascore = Ascore kernels */
+    float ms_ascore, ms_narrow_wait;    /* ms_select = best-isoform selection, ms_ascore = Ascore kernels; ms_narrow_wait = host
+                                           time the call spent waiting for the m/z narrowing pass (pa_narrow_mz) of a chunk */
     int64_t n_chunks;                   /* chunks the batch was cut into: every stage launches once per chunk */
     int64_t n_spec_exact;               /* spectra whose m/z kept an exact float64 copy beside the narrowed batch (pa_narrow_mz) */
 } pa_counters_t;
@@ -239,9 +240,12 @@ int pa_counters(const pa_scorer* s, pa_counters_t* out);
 /* Host-side helper behind the end-to-end path of host batches: out32[i] = (float)mz[i] for every peak of the CSR block and
  * exact_flag[s] = 1 for the spectra whose kernels' view would change if the float32 values were widened back -- different
  * bounds (cpp/Spectra.cpp:46-48) or a different bin for some peak (:58-60) -- which therefore keep their float64 values.
- * pa_score_batch applies it per chunk to host inputs (on a few host threads, while the previous chunk's bytes are on the
- * wire: PA_HOST_THREADS, PA_NARROW=0 turns it off) so that the link carries 4 instead of 8 bytes of m/z per peak; results
- * are bit-identical by construction and by test.  Returns the number of flagged spectra.  Needs no GPU. */
+ * pa_score_batch applies it per chunk to host inputs (on the scorer's host threads -- PA_HOST_THREADS, default min(16,
+ * usable CPUs / GPUs of the box) -- while the previous chunk's bytes are on the wire) so that the link carries 4 instead of
+ * 8 bytes of m/z per peak; results are bit-identical by construction and by test.  By default only when the scorer has at
+ * least 10 host threads, and only for as long as the pass keeps ahead of the copies: a call that spends more than 30 % of
+ * its time waiting for it switches it off for the scorer (pa_counters_t.ms_narrow_wait).  PA_NARROW=0 / 1 force it off / on.
+ * Returns the number of flagged spectra.  Needs no GPU. */
 int64_t pa_narrow_mz(const double* mz, const int64_t* spec_off, int64_t n_spec, float bin_size, float* out32,
                      uint8_t* exact_flag);
 

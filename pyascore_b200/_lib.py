@@ -39,7 +39,7 @@ class PaCounters(C.Structure):
                                          "n_fragment_lookups", "bytes_h2d", "bytes_d2h", "kernel_launches")] + \
                [(n, C.c_float) for n in ("ms_bin", "ms_plan", "ms_count", "ms_select", "ms_total")] + \
                [(n, C.c_int64) for n in ("launches_bin", "launches_count", "launches_select", "launches_ascore")] + \
-               [(n, C.c_float) for n in ("ms_ascore", "reserved")] + [("n_chunks", C.c_int64), ("n_spec_exact", C.c_int64)]
+               [(n, C.c_float) for n in ("ms_ascore", "ms_narrow_wait")] + [("n_chunks", C.c_int64), ("n_spec_exact", C.c_int64)]
 
 
 EXPORTS = ["pa_create", "pa_add_neutral_loss", "pa_destroy", "pa_last_error", "pa_score_batch",

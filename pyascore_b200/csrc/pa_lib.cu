@@ -9,6 +9,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -126,6 +127,10 @@ struct ChunkView {           // device-side views of the chunk in flight (kept f
 // vectorised), or else the reference's own formula evaluated on both values.  A spectrum that fails keeps an exact
 // float64 copy (a few per thousand on continuous data).  Runs on a small pool of host threads owned by the scorer while
 // the previous chunk's bytes are on the wire; the narrowed bytes are what the timed end-to-end region then moves.
+// Measured on a 16-core box (config 2, one GPU, `profiles/r06b_narrowing_threads.txt`): with 16 threads the pass keeps
+// ahead of the link (end to end 11.7 -> 13.7 M PSM/s), with 8 it does not (8.3 M), with 4: 8.0 M, with 2: 4.1 M.
+#define PA_NARROW_MIN_THREADS 10
+
 struct HostPool {
     std::vector<std::thread> th;
     std::mutex mu;
@@ -229,7 +234,9 @@ struct pa_scorer {
     HostPool pool;                         // host threads of the m/z narrowing pass (started on first use)
     NarrowStage nstage[3];
     int host_threads = 1;                  // PA_HOST_THREADS, default min(16, usable CPUs / GPUs of the box)
-    int narrow_mode = -1;                  // PA_NARROW: 0 never, 1 always, default: host chunks of >= 2^19 peaks
+    int narrow_mode = -1;                  // PA_NARROW: 0 never, 1 always, default: host chunks of >= 2^19 peaks when the scorer
+                                           // has PA_NARROW_MIN_THREADS (10) host threads and the pass keeps ahead of the copies
+    bool narrow_auto_off = false;          // default mode only: the pass was seen to hold the copies up (see score_impl); it stays off
     bool bin_rows = true;                  // PA_K1=topn: k_bin_topn alone (the row form k_bin_rows off)
     // pa_score_batch_async: the scorer's own orchestration thread (started on first use, parked between calls: a
     // fresh thread per call would pay thread creation and the CUDA runtime's per-thread set-up every time)
@@ -899,7 +906,7 @@ static int narrow_begin(pa_scorer* s, NarrowStage& ns, const pa_batch* in, const
     ns.ok = false; ns.busy = false;
     ns.s0 = r.s0; ns.ns = r.s1 - r.s0;
     ns.peak_lo = in->spec_off[r.s0]; ns.npk = in->spec_off[r.s1] - ns.peak_lo;
-    if (ns.ns <= 0 || !(s->narrow_mode == 1 || (s->narrow_mode < 0 && ns.npk >= (1 << 19) && s->host_threads >= 2))) return PA_OK;
+    if (ns.ns <= 0 || !(s->narrow_mode == 1 || (s->narrow_mode < 0 && !s->narrow_auto_off && ns.npk >= (1 << 19) && s->host_threads >= PA_NARROW_MIN_THREADS))) return PA_OK;
     CK(cudaEventSynchronize(ns.ev));                      // the chunk that used this set three chunks ago has left it
     CK(ensure_pinned_t(ns.h_mz32, ns.h_mz32_cap, (size_t)ns.npk));
     CK(ensure_pinned_t(ns.h_escoff, ns.h_escoff_cap, (size_t)ns.ns));
@@ -923,7 +930,11 @@ static int narrow_begin(pa_scorer* s, NarrowStage& ns, const pa_batch* in, const
 
 static int narrow_end(pa_scorer* s, NarrowStage& ns, const pa_batch* in) {
     if (!ns.busy) return PA_OK;
-    s->pool.wait();
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        s->pool.wait();
+        s->ctr.ms_narrow_wait += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     ns.busy = false;
     ns.n_esc = 0; ns.n_flag = 0;
     for (int64_t q = 0; q < ns.ns; q++)
@@ -1369,6 +1380,7 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
         return fail(s, PA_ERR_ARG, "NULL input array");
     CK(cudaSetDevice(s->device));
     int rc = PA_OK;         // (the device-side config is current: pa_create / pa_add_neutral_loss refresh it)
+    const auto t_call = std::chrono::steady_clock::now();
     memset(&s->ctr, 0, sizeof(s->ctr));
     s->ev_used = 0;
     s->kept.valid = false;
@@ -1508,7 +1520,17 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
                 const char* why = prepare_host_chunk(c + 1);
                 if (why) { bail(0); return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why); }
             }
-            if (may_narrow) { rc = narrow_end(s, nstage(c + 1), in); if (rc != PA_OK) return bail(rc); }
+            if (may_narrow) {
+                rc = narrow_end(s, nstage(c + 1), in);
+                if (rc != PA_OK) return bail(rc);
+                // The pass is only worth its bytes while it hides behind the copies.  If this call has spent more than
+                // 30 % of its time waiting for it, the host is the slower side (few threads for this GPU, or a memory
+                // system shared with other ranks): later chunks and calls send float64 (default mode only).
+                if (s->narrow_mode < 0 && !s->narrow_auto_off && c >= 1) {
+                    const float spent = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+                    if (s->ctr.ms_narrow_wait > 0.3f * spent) s->narrow_auto_off = true;
+                }
+            }
             // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
             rc = chunk_front(s, (int)((c + 1) & 1), in, in_dev, chunks[c + 1], mod_lo[c + 1], mod_hi[c + 1],
                              chunk_maxp[c + 1], cs[c + 1], in_dev ? &ends_dev[c + 1] : nullptr, may_narrow ? &nstage(c + 1) : nullptr);

@@ -12,12 +12,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock
 PER=$(python - <<PY
 import csv,re
 rows=[r for r in csv.reader(open("gpurun_out/${TAG}_launches_lowres_262144.csv")) if len(r)>12 and r[0].isdigit() and r[12].startswith("gpu__time_duration")]
-names=[r[4].split("(")[0] for r in rows if re.search(r"k_bin_topn|k_count_score|k_select|k_ascore", r[4])]
-idx=[i for i,n in enumerate(names) if "k_bin_topn" in n]
+names=[r[4].split("(")[0] for r in rows if re.search(r"k_bin_|k_count_score|k_select|k_ascore", r[4])]
+idx=[i for i,n in enumerate(names) if "k_bin_rows" in n]
 print(idx[1]-idx[0] if len(idx)>1 else len(names))
 PY
 )
 echo "kernels per step: $PER"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_bin_topn|k_count_score|k_select|k_ascore' -s $((PER*3)) -c $PER \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_bin_|k_count_score|k_select|k_ascore' -s $((PER*3)) -c $PER \
     -f -o gpurun_out/${TAG}_prof_lowres $PROF > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full.log | cut -c1-200

@@ -10,15 +10,15 @@ timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock
 # capture the 4th step (3 warm-ups come first)
 PER=$(python - <<PY
 import csv,re
-rows=[r for r in csv.reader(open("gpurun_out/${TAG}_launches_${W}.csv")) if len(r)>5 and re.search(r"k_bin_topn|k_count_score|k_select|k_ascore", r[4] if len(r)>4 else "")]
+rows=[r for r in csv.reader(open("gpurun_out/${TAG}_launches_${W}.csv")) if len(r)>5 and re.search(r"k_bin_|k_count_score|k_select|k_ascore", r[4] if len(r)>4 else "")]
 names=[r[4].split("(")[0] for r in rows if r[-3].startswith("gpu__time_duration")]
-# one step = from one k_bin_topn to the next
-idx=[i for i,n in enumerate(names) if "k_bin_topn" in n]
+# one step = from one k_bin_rows to the next
+idx=[i for i,n in enumerate(names) if "k_bin_rows" in n]
 print(idx[1]-idx[0] if len(idx)>1 else len(names))
 PY
 )
 echo "kernels per step: $PER"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_bin_topn|k_count_score|k_select|k_ascore' -s $((PER*3)) -c $PER \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_bin_|k_count_score|k_select|k_ascore' -s $((PER*3)) -c $PER \
     -f -o gpurun_out/${TAG}_prof_${W} $PROF > gpurun_out/${TAG}_ncu_full_${W}.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full_${W}.log | cut -c1-200
 ls -la gpurun_out | grep ${TAG}

@@ -17,7 +17,7 @@ for r in body:
     tot = 0.
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[ix[m]].replace(",", "")) * scale[units[ix[m]]]
-    key = ("bin_topn" if name.startswith("k_bin_topn") else "select" if name.startswith("k_select") else
+    key = ("bin_topn" if name.startswith("k_bin_") else "select" if name.startswith("k_select") else
            "count_score" if name.startswith("k_count_score") else "ascore" if name.startswith("k_ascore") else name)
     e = out.setdefault(key, {"dram_bytes_per_psm": 0., "warp_inst_per_psm": 0., "kernels": []})
     e["dram_bytes_per_psm"] += tot / n
