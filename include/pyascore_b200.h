@@ -242,9 +242,10 @@ int pa_counters(const pa_scorer* s, pa_counters_t* out);
  * bounds (cpp/Spectra.cpp:46-48) or a different bin for some peak (:58-60) -- which therefore keep their float64 values.
  * pa_score_batch applies it per chunk to host inputs (on the scorer's host threads -- PA_HOST_THREADS, default min(16,
  * usable CPUs / GPUs of the box) -- while the previous chunk's bytes are on the wire) so that the link carries 4 instead of
- * 8 bytes of m/z per peak; results are bit-identical by construction and by test.  By default only when the scorer has at
- * least 10 host threads, and only for as long as the pass keeps ahead of the copies: a call that spends more than 30 % of
- * its time waiting for it switches it off for the scorer (pa_counters_t.ms_narrow_wait).  PA_NARROW=0 / 1 force it off / on.
+ * 8 bytes of m/z per peak; results are bit-identical by construction and by test.  By default a scorer with at least 10
+ * host threads decides by measurement: of its first large host batches (>= 2^20 peaks) the first two narrow, the third does
+ * not, and the faster way (peaks per second of the whole call) is kept.  PA_NARROW=0 / 1 force it off / on;
+ * pa_counters_t.ms_narrow_wait is the time a call waited for the pass.
  * Returns the number of flagged spectra.  Needs no GPU. */
 int64_t pa_narrow_mz(const double* mz, const int64_t* spec_off, int64_t n_spec, float bin_size, float* out32,
                      uint8_t* exact_flag);

@@ -236,7 +236,9 @@ struct pa_scorer {
     int host_threads = 1;                  // PA_HOST_THREADS, default min(16, usable CPUs / GPUs of the box)
     int narrow_mode = -1;                  // PA_NARROW: 0 never, 1 always, default: host chunks of >= 2^19 peaks when the scorer
                                            // has PA_NARROW_MIN_THREADS (10) host threads and the pass keeps ahead of the copies
-    bool narrow_auto_off = false;          // default mode only: the pass was seen to hold the copies up (see score_impl); it stays off
+    int narrow_state = 0;                  // default mode: 0 first (cold) narrowed call, 1 timed with the pass, 2 timed without, 3 decided
+    double narrow_rate_on = 0.;            //   peaks per second of the timed call with the pass
+    bool narrow_keep = true;               //   the decision (see score_impl)
     bool bin_rows = true;                  // PA_K1=topn: k_bin_topn alone (the row form k_bin_rows off)
     // pa_score_batch_async: the scorer's own orchestration thread (started on first use, parked between calls: a
     // fresh thread per call would pay thread creation and the CUDA runtime's per-thread set-up every time)
@@ -906,7 +908,7 @@ static int narrow_begin(pa_scorer* s, NarrowStage& ns, const pa_batch* in, const
     ns.ok = false; ns.busy = false;
     ns.s0 = r.s0; ns.ns = r.s1 - r.s0;
     ns.peak_lo = in->spec_off[r.s0]; ns.npk = in->spec_off[r.s1] - ns.peak_lo;
-    if (ns.ns <= 0 || !(s->narrow_mode == 1 || (s->narrow_mode < 0 && !s->narrow_auto_off && ns.npk >= (1 << 19) && s->host_threads >= PA_NARROW_MIN_THREADS))) return PA_OK;
+    if (ns.ns <= 0 || !(s->narrow_mode == 1 || (s->narrow_mode < 0 && ns.npk >= (1 << 19)))) return PA_OK;
     CK(cudaEventSynchronize(ns.ev));                      // the chunk that used this set three chunks ago has left it
     CK(ensure_pinned_t(ns.h_mz32, ns.h_mz32_cap, (size_t)ns.npk));
     CK(ensure_pinned_t(ns.h_escoff, ns.h_escoff_cap, (size_t)ns.ns));
@@ -1502,7 +1504,14 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
     // The m/z narrowing of a host chunk (narrow_begin / narrow_end) runs on the pool one chunk AHEAD of the copies: the
     // set of chunk c+2 is being filled while chunk c+1 is on the wire and this thread waits for chunk c's plan, so the
     // copy engine never waits for a conversion.  Three staging sets rotate; a set is reused once its copies are done.
-    const bool may_narrow = !in_dev && !(chunks.size() == 1 && s->narrow_mode != 1 && in->spec_off[chunks[0].s1] - in->spec_off[chunks[0].s0] < (1 << 19));
+    // Default mode decides by measurement whether the pass pays on this box: the scorer's first large host batch narrows
+    // (and pins the staging buffers, starts the threads), the second narrows and is timed, the third does not and is
+    // timed, and the faster way (peaks per second of the whole call) is kept.  It needs PA_NARROW_MIN_THREADS to try.
+    const int64_t call_peaks = in_dev || chunks.empty() ? 0 : in->spec_off[chunks.back().s1] - in->spec_off[chunks[0].s0];
+    const bool narrow_trial = s->narrow_mode < 0 && !in_dev && call_peaks >= (1 << 20) && s->host_threads >= PA_NARROW_MIN_THREADS;
+    const bool want_narrow = s->narrow_mode == 1 || (narrow_trial && (s->narrow_state <= 1 || (s->narrow_state == 3 && s->narrow_keep)));
+    const bool may_narrow = !in_dev && want_narrow &&
+                            !(chunks.size() == 1 && s->narrow_mode != 1 && in->spec_off[chunks[0].s1] - in->spec_off[chunks[0].s0] < (1 << 19));
     auto nstage = [&](size_t c) -> NarrowStage& { return s->nstage[c % 3]; };
     auto bail = [&](int code) { if (may_narrow) for (int i = 0; i < 3; i++) if (s->nstage[i].busy) { s->pool.wait(); s->nstage[i].busy = false; } cudaDeviceSynchronize(); return code; };
     if (may_narrow) {
@@ -1523,13 +1532,6 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
             if (may_narrow) {
                 rc = narrow_end(s, nstage(c + 1), in);
                 if (rc != PA_OK) return bail(rc);
-                // The pass is only worth its bytes while it hides behind the copies.  If this call has spent more than
-                // 30 % of its time waiting for it, the host is the slower side (few threads for this GPU, or a memory
-                // system shared with other ranks): later chunks and calls send float64 (default mode only).
-                if (s->narrow_mode < 0 && !s->narrow_auto_off && c >= 1) {
-                    const float spent = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_call).count();
-                    if (s->ctr.ms_narrow_wait > 0.3f * spent) s->narrow_auto_off = true;
-                }
             }
             // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
             rc = chunk_front(s, (int)((c + 1) & 1), in, in_dev, chunks[c + 1], mod_lo[c + 1], mod_hi[c + 1],
@@ -1560,6 +1562,12 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
     }
     cudaEventElapsedTime(&s->ctr.ms_total, e_all0, e_all1);
     s->ctr.n_fragment_lookups = (int64_t)(*s->slot[0].h_lookups) + (int64_t)(*s->slot[1].h_lookups);
+    if (narrow_trial && s->narrow_state < 3) {
+        const double rate = (double)call_peaks / std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
+        if (s->narrow_state == 1) s->narrow_rate_on = rate;
+        else if (s->narrow_state == 2) s->narrow_keep = s->narrow_rate_on > 1.02 * rate;
+        s->narrow_state++;
+    }
     return PA_OK;
 }
 
