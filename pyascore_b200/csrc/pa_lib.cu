@@ -293,6 +293,7 @@ static void bin_launch_shape(int sm_count, int64_t max_peaks, int64_t n_spec, in
 }
 
 // Launch shape of k_bin_rows: slots of up to PA_ROWS_MAXCAP peaks (larger spectra are declined to k_bin_topn)
+#define PA_ROWS_MIN_SPECTRA 256
 typedef void (*bin_rows_fn)(PaBinArgs);
 static bin_rows_fn bin_rows_kernel(bool f32, bool narrow) {
     return f32 ? (narrow ? k_bin_rows<true, true> : k_bin_rows<true, false>) : (narrow ? k_bin_rows<false, true> : k_bin_rows<false, false>);
@@ -1063,7 +1064,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     cs.e_bin0 = next_event(s); cs.e_bin1 = next_event(s); cs.e_plan1 = next_event(s);
     CK(cudaEventRecord(cs.e_bin0, st));
     ba.list = nullptr; ba.list_n = nullptr;
-    if (ns > 0 && s->bin_rows && s->n_top <= 31) {
+    if (ns >= PA_ROWS_MIN_SPECTRA && s->bin_rows && s->n_top <= 31) {     // (a handful of spectra: one launch instead of two)
         // the row form takes the spectra that are the rule and lists the rest, which k_bin_topn then takes from the list
         CK(sl.bin_list.ensure((size_t)ns * sizeof(int32_t)));
         CK(sl.bin_list_n.ensure(sizeof(unsigned int)));
