@@ -3,7 +3,7 @@
 # usage: tools/gpu_prof_workload.sh <tag> <workload> [psms]
 TAG=$1; W=$2; N=${3:-262144}
 mkdir -p gpurun_out
-PROF="python bench.py --workload $W --psms $N --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+PROF="python bench.py --workload $W --psms $N --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-configs"
 timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches_${W}.csv $PROF > gpurun_out/${TAG}_ncu_launch_${W}.log 2>&1
 # kernels of the path per step: find how many matching launches one step has from the launch list, then
