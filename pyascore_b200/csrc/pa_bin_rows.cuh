@@ -1,5 +1,5 @@
-// K1 "row form": BinnedSpectra for the spectra that are the rule -- m/z ascending, at most PA_ROWS_MAXCAP peaks, a sane
-// m/z range, n_top <= 31.  cpp/Spectra.cpp:43-68 (bounds + bin index), :24-41 (top n_top of every bin by intensity).
+// K1 "row form": BinnedSpectra for the spectra that are the rule -- m/z ascending, at most PA_ROWS_MAXCAP peaks (fewer than
+// 512 in any one bin), a sane m/z range, n_top <= 31.  cpp/Spectra.cpp:43-68 (bounds + bin index), :24-41 (top n_top of every bin by intensity).
 //
 // One warp per spectrum, two passes of one peak per lane and 32 peaks per round, nothing staged.  A round of the binning
 // pass reads its 32 m/z and intensities straight from global memory (coalesced 8- or 4-byte loads, the next round's already
@@ -19,7 +19,7 @@
 #pragma once
 #include <type_traits>
 
-#define PA_ROWS_MAXCAP 512
+#define PA_ROWS_MAXCAP 1024
 // per warp: key f32[cap + 4] | mzf f32[cap] | bin u8[cap] | range u32[132] | cell u32[256]
 #define PA_ROWS_RANGE_BYTES ((PA_NBIN_SMEM + 4) * 4)
 #define PA_ROWS_SLOT_BYTES(cap) ((size_t)(cap) * 9 + 16 + PA_ROWS_RANGE_BYTES + PA_NCELL * 4)
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
             const uint32_t rg = pa_lds32(S_RANGE + 4 * b);
             const uint32_t b0 = rg & 0xffffu, bl = (rg >> 16) - 1u;          // first and last peak of the run
             const int n = (int)(rg >> 16) - (int)b0;
-            want += (n * (n - 1)) >> 1;
+            want += n < 512 ? (n * (n - 1)) >> 1 : -1000000;                 // (pa_gt_count counts up to 511: a larger run declines)
             const uint32_t a0 = b0 & ~3u, al = bl & ~3u;
             uint32_t mf = (0xfu << (b0 & 3u)) & 0xfu;
             uint32_t ml = 0xfu >> (3u - (bl & 3u));

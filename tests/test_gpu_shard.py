@@ -304,3 +304,22 @@ def test_row_form_binning_equals_topn_kernel(workload, n, f32, monkeypatch):
         s.close()
     assert _same(res["topn"], res["rows"])
     assert res["rows_launches"] == 2 * res["topn_launches"]
+
+
+def test_row_form_binning_large_spectra(monkeypatch):
+    """spectra of 500 .. 900 peaks (the row form's slot holds up to 1024) and one spectrum whose peaks all fall into one
+    bin (more than 511 peaks in a run: declined, the count decode of the row form stops at 511)"""
+    from pyascore_b200 import Scorer
+    w = dict(synth.WORKLOADS["lowres_phospho"], noise=(500, 900))
+    batch = synth.make_batch(w, 1500, seed=5)
+    off, mz = batch["spec_off"], batch["mz"]
+    a, b = int(off[3]), int(off[4])
+    mz[a:b] = np.sort(np.random.default_rng(1).uniform(400.5, 499.5, b - a))
+    assert b - a > 511
+    res = {}
+    for mode in ("topn", "rows"):
+        monkeypatch.setenv("PA_K1", mode)
+        s = Scorer(**w["scorer"])
+        res[mode] = s.score_batch(dict(batch))
+        s.close()
+    assert _same(res["topn"], res["rows"])
