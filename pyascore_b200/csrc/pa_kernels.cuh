@@ -743,7 +743,8 @@ __device__ __forceinline__ void pa_walk_fast(const PaCfg& cfg, const PaFastCtx& 
     float run = 0.f;
     int nls = 0;
     // replay of the running sum up to the lane's segment (the adds must stay sequential: the reference's rounding)
-    for (int step = 0; step < s0; step++) {
+    // (both loops count down: a bound derived from the lane would be recomputed at every trip under this register budget)
+    for (int n = s0; n > 0; n--) {
         const uint32_t st = (uint32_t)w & 1u;
         w >>= 1;
         run = __fadd_rn(pa_lds_f32(ra + 4u * st), run);
@@ -755,7 +756,7 @@ __device__ __forceinline__ void pa_walk_fast(const PaCfg& cfg, const PaFastCtx& 
         ra += dr;
     }
     const int Z = c.Z;
-    for (int step = s0; step < s1; step++) {
+    for (int n = s1 - s0; n > 0; n--) {
         const uint32_t st = (uint32_t)w & 1u;
         w >>= 1;
         run = __fadd_rn(pa_lds_f32(ra + 4u * st), run);
