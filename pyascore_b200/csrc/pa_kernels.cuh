@@ -739,7 +739,11 @@ __device__ __forceinline__ void pa_walk_fast(const PaCfg& cfg, const PaFastCtx& 
     uint64_t w = fwd ? mlo : (__brevll(mlo) >> (64 - c.L));
     uint32_t ra = fwd ? c.res_a : c.res_a + 8u * (uint32_t)(c.L - 1);
     uint32_t na = fwd ? c.nli_a : c.nli_a + 2u * (uint32_t)(c.L - 1);
-    const int dr = fwd ? 8 : -8, dn = fwd ? 2 : -2;
+    int dr = fwd ? 8 : -8, dn = fwd ? 2 : -2;
+    // (values derived from the lane are otherwise recomputed at every trip under this register budget -- ~20 instructions
+    // per step: an empty asm makes them opaque, so they stay in their registers)
+    asm volatile("" : "+r"(dr));
+    if (HAS_NL) asm volatile("" : "+r"(dn));
     float run = 0.f;
     int nls = 0;
     // replay of the running sum up to the lane's segment (the adds must stay sequential: the reference's rounding)
