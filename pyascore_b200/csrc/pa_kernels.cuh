@@ -728,8 +728,11 @@ __device__ __forceinline__ void pa_fast_lookup(const PaFastCtx& c, float f, int 
 }
 
 template <bool HAS_NL, bool EGH>
-__device__ __forceinline__ void pa_walk_fast(const PaCfg& cfg, const PaFastCtx& c, uint64_t mlo, char type, int s0, int s1,
+__device__ __forceinline__ void pa_walk_fast(const PaCfg& cfg, const PaFastCtx& c0, uint64_t mlo, char type, int s0, int s1,
                                              unsigned long long& clo, unsigned long long& chi, uint32_t& nfrag) {
+    PaFastCtx c = c0;
+    // (see below: kept in registers instead of being rebuilt per lookup; measured to pay only in the neutral-loss form)
+    if (HAS_NL) { asm volatile("" : "+r"(c.lut_a)); asm volatile("" : "+r"(c.nl_a)); }
     clo = 0; chi = 0; nfrag = 0;
     const bool fwd = (type == 'b' || type == 'c');
     double a1, a2;
