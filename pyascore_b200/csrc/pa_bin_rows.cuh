@@ -20,6 +20,9 @@
 #include <type_traits>
 
 #define PA_ROWS_MAXCAP 1024
+#ifndef PA_K1_MINBLOCKS
+#define PA_K1_MINBLOCKS 4      // 64 registers: 32 warps per SM (3 -> 80 registers, 5 -> 48: measured)
+#endif
 // per warp: key f32[cap + 4] | mzf f32[cap] | bin u8[cap] | range u32[132] | cell u32[256]
 #define PA_ROWS_RANGE_BYTES ((PA_NBIN_SMEM + 4) * 4)
 #define PA_ROWS_SLOT_BYTES(cap) ((size_t)(cap) * 9 + 16 + PA_ROWS_RANGE_BYTES + PA_NCELL * 4)
@@ -67,7 +70,7 @@ __device__ __forceinline__ void pa_prefetch_l2(const void* p) { asm volatile("pr
 
 // F32: float32 intensities (pa_batch.inten32).  NARROW: float32 m/z from the host's narrowing pass (pa_narrow_mz).
 template <bool F32, bool NARROW>
-__global__ void __launch_bounds__(256, 4) k_bin_rows(PaBinArgs a) {
+__global__ void __launch_bounds__(256, PA_K1_MINBLOCKS) k_bin_rows(PaBinArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename std::conditional<NARROW, float, double>::type mz_t;
     typedef typename std::conditional<F32, float, double>::type in_t;
