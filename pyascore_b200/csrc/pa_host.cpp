@@ -1,6 +1,7 @@
 // Host arithmetic of libpyascore_b200 that wants the host compiler's vector units: the m/z narrowing pass
 // (see pa_lib.cu "host-side narrowing of the m/z array" for what it proves and why it is sound).
 // AVX2 when the CPU has it (checked at run time), plain C++ otherwise; both give the same flags.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <immintrin.h>
@@ -70,22 +71,39 @@ __attribute__((target("avx2"))) Extremes fused_avx2(const double* m, int64_t P, 
     const __m256d vd = _mm256_set1_pd(dmin), vi = _mm256_set1_pd(inv), ve = _mm256_set1_pd(eps), v1 = _mm256_set1_pd(1. - eps);
     __m256d mn = _mm256_set1_pd(m[0]), mx = mn, bad = _mm256_setzero_pd(), acc = _mm256_setzero_pd();
     int64_t i = 0;
-    for (; i + 4 <= P; i += 4) {
-        const __m256d v = _mm256_loadu_pd(m + i);
-        _mm_storeu_ps(out + i, _mm256_cvtpd_ps(v));
-        mn = _mm256_min_pd(mn, v);
-        mx = _mm256_max_pd(mx, v);
-        const __m256d d = _mm256_sub_pd(v, v);
-        bad = _mm256_or_pd(bad, _mm256_cmp_pd(d, d, _CMP_UNORD_Q));
-        const __m256d t = _mm256_mul_pd(_mm256_sub_pd(v, vd), vi);
-        const __m256d r = _mm256_sub_pd(t, _mm256_floor_pd(t));
-        acc = _mm256_or_pd(acc, _mm256_or_pd(_mm256_cmp_pd(r, ve, _CMP_LT_OQ), _mm256_cmp_pd(r, v1, _CMP_GT_OQ)));
+    // The float32 copy is written once and next read by the copy engine: streaming stores from the first 16-byte aligned
+    // element on keep it out of the caches and spare the read-for-ownership of the destination lines (the pass shares
+    // the host's memory system with the DMA it feeds).  pa_narrow_spectra fences before it returns.
+    const int64_t head = std::min<int64_t>(P, (int64_t)((32 - ((uintptr_t)out & 31)) & 31) / 4);
+    if (head > 0) {
+        Extremes h = convert_scalar(m, head, out, 0, e);
+        *near_out = near_scalar(m, head, 0, dmin, inv, eps);
+        mn = _mm256_set1_pd(h.mn); mx = _mm256_set1_pd(h.mx);
+        if (h.bad) bad = _mm256_castsi256_pd(_mm256_set1_epi64x(-1));
+        i = head;
+    } else *near_out = 0;
+#define PA_LANE4(v)                                                                                                       \
+    do {                                                                                                                  \
+        mn = _mm256_min_pd(mn, v);                                                                                        \
+        mx = _mm256_max_pd(mx, v);                                                                                        \
+        const __m256d d_ = _mm256_sub_pd(v, v);                                                                           \
+        bad = _mm256_or_pd(bad, _mm256_cmp_pd(d_, d_, _CMP_UNORD_Q));                                                     \
+        const __m256d t_ = _mm256_mul_pd(_mm256_sub_pd(v, vd), vi);                                                       \
+        const __m256d r_ = _mm256_sub_pd(t_, _mm256_floor_pd(t_));                                                        \
+        acc = _mm256_or_pd(acc, _mm256_or_pd(_mm256_cmp_pd(r_, ve, _CMP_LT_OQ), _mm256_cmp_pd(r_, v1, _CMP_GT_OQ)));      \
+    } while (0)
+    for (; i + 8 <= P; i += 8) {
+        const __m256d va = _mm256_loadu_pd(m + i), vb = _mm256_loadu_pd(m + i + 4);
+        _mm256_stream_ps(out + i, _mm256_set_m128(_mm256_cvtpd_ps(vb), _mm256_cvtpd_ps(va)));
+        PA_LANE4(va);
+        PA_LANE4(vb);
     }
+#undef PA_LANE4
     double a[4], b[4];
     _mm256_storeu_pd(a, mn); _mm256_storeu_pd(b, mx);
     for (int k = 0; k < 4; k++) { e.mn = a[k] < e.mn ? a[k] : e.mn; e.mx = b[k] > e.mx ? b[k] : e.mx; }
     e.bad = _mm256_movemask_pd(bad) != 0;
-    *near_out = (_mm256_movemask_pd(acc) != 0) | near_scalar(m, P, i, dmin, inv, eps);
+    *near_out |= (_mm256_movemask_pd(acc) != 0) | near_scalar(m, P, i, dmin, inv, eps);
     return convert_scalar(m, P, out, i, e);
 }
 
@@ -134,4 +152,5 @@ void pa_narrow_spectra(const double* mz, const int64_t* spec_off, int64_t sa, in
         }
         flag[s] = (uint8_t)(bad != 0);
     }
+    _mm_sfence();          // the streaming stores above are globally visible before the caller hands the buffer on
 }
