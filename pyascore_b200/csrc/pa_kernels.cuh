@@ -1,6 +1,7 @@
 // Kernels of libpyascore_b200 (sm_100a).  The unit of domain work decides who owns it:
 //   K0  k_tail_table     one block per trial count n: float32-faithful binomial score table
-//   K1  k_bin_topn       one warp per spectrum: top-n_top peaks per bin_size-Th bin (BinnedSpectra)
+//   K1  k_bin_rows       one warp per spectrum: top-n_top peaks per bin_size-Th bin (BinnedSpectra), row form for the
+//                        spectra that are the rule (pa_bin_rows.cuh); k_bin_topn takes the ones it declines
 //   P1  k_plan           one thread per PSM: validation, #sites, #isoforms, work units
 //   K2  k_count_score    one warp per unit of <=1024 positional isoforms: fragments, matches, PepScore
 //   K3a k_select_thread  one thread per PSM: reference-order best isoform, tied competitors per site,
