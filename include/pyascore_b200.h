@@ -241,7 +241,7 @@ int pa_counters(const pa_scorer* s, pa_counters_t* out);
  * exact_flag[s] = 1 for the spectra whose kernels' view would change if the float32 values were widened back -- different
  * bounds (cpp/Spectra.cpp:46-48) or a different bin for some peak (:58-60) -- which therefore keep their float64 values.
  * pa_score_batch applies it per chunk to host inputs (on the scorer's host threads -- PA_HOST_THREADS, default min(16,
- * usable CPUs / GPUs of the box) -- while the previous chunk's bytes are on the wire) so that the link carries 4 instead of
+ * the process's CPUs / (scorers alive in it x LOCAL_WORLD_SIZE)) -- while the previous chunk's bytes are on the wire) so that the link carries 4 instead of
  * 8 bytes of m/z per peak; results are bit-identical by construction and by test.  By default a scorer with at least 10
  * host threads decides by measurement: of its first large host batches (>= 2^20 peaks) the first two narrow, the third does
  * not, and the faster way (peaks per second of the whole call) is kept.  PA_NARROW=0 / 1 force it off / on;

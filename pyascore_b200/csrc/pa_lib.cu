@@ -9,6 +9,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -127,6 +128,17 @@ struct ChunkView {           // device-side views of the chunk in flight (kept f
 // vectorised), or else the reference's own formula evaluated on both values.  A spectrum that fails keeps an exact
 // float64 copy (a few per thousand on continuous data).  Runs on a small pool of host threads owned by the scorer while
 // the previous chunk's bytes are on the wire; the narrowed bytes are what the timed end-to-end region then moves.
+// Host threads of one scorer's narrowing pool when PA_HOST_THREADS does not say: the CPUs this process may run on, shared
+// between the scorers alive in it (MultiScorer: one per GPU) and the processes of the job on this node (one rank per GPU
+// under torchrun: LOCAL_WORLD_SIZE), at most 16.  Settled when the pool starts.
+static std::atomic<int> g_live_scorers{0};
+static int host_thread_budget(int cpus) {
+    int procs = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) procs = std::max(1, atoi(e));
+    const int scorers = std::max(1, g_live_scorers.load());
+    return std::max(1, std::min(16, cpus / (procs * scorers)));
+}
+
 // Measured on a 16-core box (config 2, one GPU, `profiles/r06b_narrowing_threads.txt`): with 16 threads the pass keeps
 // ahead of the link (end to end 11.7 -> 13.7 M PSM/s), with 8 it does not (8.3 M), with 4: 8.0 M, with 2: 4.1 M.
 #define PA_NARROW_MIN_THREADS 10
@@ -233,7 +245,9 @@ struct pa_scorer {
     bool binner_only = false;
     HostPool pool;                         // host threads of the m/z narrowing pass (started on first use)
     NarrowStage nstage[3];
-    int host_threads = 1;                  // PA_HOST_THREADS, default min(16, usable CPUs / GPUs of the box)
+    int host_threads = 1;                  // PA_HOST_THREADS; default: see host_thread_budget
+    int host_cpus = 1;                     // CPUs this process may run on
+    bool host_threads_fixed = false;
     int narrow_mode = -1;                  // PA_NARROW: 0 never, 1 always, default: host chunks of >= 2^19 peaks when the scorer
                                            // has PA_NARROW_MIN_THREADS (10) host threads and the pass keeps ahead of the copies
     int narrow_state = 0;                  // default mode: 0 first (cold) narrowed call, 1 timed with the pass, 2 timed without, 3 decided
@@ -632,12 +646,14 @@ static int create_scorer(float bin_size, int n_top, const char* mod_group, float
     s = new pa_scorer();
     s->device = device;
     s->binner_only = binner_only;
+    if (!binner_only) g_live_scorers++;
     {
         int cpus = (int)std::thread::hardware_concurrency();
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
-        s->host_threads = std::max(1, std::min(16, cpus / std::max(ndev, 1)));
-        if (const char* e = getenv("PA_HOST_THREADS")) s->host_threads = std::max(1, std::min(64, atoi(e)));
+        s->host_cpus = std::max(1, cpus);
+        s->host_threads = std::max(1, std::min(16, cpus / std::max(ndev, 1)));       // (settled at the pool's start: host_thread_budget)
+        if (const char* e = getenv("PA_HOST_THREADS")) { s->host_threads = std::max(1, std::min(64, atoi(e))); s->host_threads_fixed = true; }
         if (const char* e = getenv("PA_K1")) s->bin_rows = strcmp(e, "topn") != 0;
         if (const char* e = getenv("PA_NARROW")) s->narrow_mode = (e[0] == '0') ? 0 : (e[0] == '1' ? 1 : -1);
     }
@@ -739,6 +755,7 @@ extern "C" void pa_destroy(pa_scorer* s) {
     s->d_T.release(); s->d_logd.release(); s->d_binom.release(); s->d_nl_sums.release(); s->d_nl_nvar.release();
     s->d_perm_pool.release(); s->d_perm_off.release(); s->d_lut.release();
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+    if (!s->binner_only) g_live_scorers--;
     delete s;
 }
 
@@ -981,7 +998,7 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
     const size_t pack_bytes = (size_t)(ns + 1) * 8 + (size_t)npk * (in->inten32 ? 12 : 16) + (size_t)np * 12 + (size_t)(np + 1) * 16 +
                               (size_t)(pep_hi - pep_lo) + (size_t)n_aux * 8 + 16 * 16;
     bool narrowed = false;
-    cs.packed = !in_dev && cs.single_chunk && pack_bytes <= PA_PACK_MAX && s->narrow_mode != 1;
+    cs.packed = !in_dev && cs.single_chunk && pack_bytes <= PA_PACK_MAX && s->narrow_mode != 1 && !(nst != nullptr && nst->busy);
     if (cs.packed) {
         CK(ensure_pinned(sl.h_pack, sl.h_pack_cap, pack_bytes));
         CK(sl.d_pack.ensure(pack_bytes));
@@ -1002,8 +1019,23 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
         *h2d += (int64_t)pk.used;
     } else {
     CK(stage_in(sl.spec_off, in->spec_off, in_dev, r.s0, ns + 1, st, &b.spec_off, h2d));
+    if (in->inten32) CK(stage_in(sl.inten32, in->inten32, in_dev, peak_lo, npk, st, &v_int32, h2d));
+    else CK(stage_in(sl.inten, in->inten, in_dev, peak_lo, npk, st, &v_int, h2d));
+    CK(stage_in(sl.psm_spec, in->psm_spec, in_dev, r.p0, np, st, &b.psm_spec, h2d));
+    CK(stage_in(sl.pep_off, in->pep_off, in_dev, r.p0, np + 1, st, &b.pep_off, h2d));
+    CK(stage_in(sl.pep, in->pep, in_dev, pep_lo, pep_hi - pep_lo, st, &b.pep, h2d));
+    CK(stage_in(sl.n_mod, in->n_mod, in_dev, r.p0, np, st, &b.n_mod, h2d));
+    CK(stage_in(sl.max_charge, in->max_charge, in_dev, r.p0, np, st, &b.max_charge, h2d));
+    CK(stage_in(sl.aux_off, in->aux_off, in_dev, r.p0, np + 1, st, &b.aux_off, h2d));
+    if (in->aux_off) {
+        CK(stage_in(sl.aux_pos, in->aux_pos, in_dev, aux_lo, aux_hi - aux_lo, st, &b.aux_pos, h2d));
+        CK(stage_in(sl.aux_mass, in->aux_mass, in_dev, aux_lo, aux_hi - aux_lo, st, &b.aux_mass, h2d));
+    } else { b.aux_pos = nullptr; b.aux_mass = nullptr; }
+    CK(stage_in(sl.mod_off, in->mod_off, in_dev, r.p0, np + 1, st, &cs.mod_off_abs, h2d));
     // host batches: the m/z array goes over the link as float32 wherever the host proved that nothing the kernels
-    // derive from it changes (narrow_begin / narrow_end below); spectra that failed the proof come with an exact copy
+    // derive from it changes (narrow_begin / narrow_end); spectra that failed the proof come with an exact copy.  It goes
+    // last: the chunk's other arrays are on the wire while the pool finishes the chunk's narrowing.
+    if (nst != nullptr && nst->busy) { const int nrc = narrow_end(s, *nst, in); if (nrc != PA_OK) return nrc; }
     if (nst != nullptr && nst->ok) {
         CK(sl.mz32.ensure((size_t)std::max<int64_t>(npk, 1) * 4));
         CK(sl.escoff.ensure((size_t)ns * 4));
@@ -1018,19 +1050,6 @@ static int chunk_front(pa_scorer* s, int si, const pa_batch* in, bool in_dev, co
         v_mz = nullptr;
     }
     if (!narrowed) CK(stage_in(sl.mz, in->mz, in_dev, peak_lo, npk, st, &v_mz, h2d));
-    if (in->inten32) CK(stage_in(sl.inten32, in->inten32, in_dev, peak_lo, npk, st, &v_int32, h2d));
-    else CK(stage_in(sl.inten, in->inten, in_dev, peak_lo, npk, st, &v_int, h2d));
-    CK(stage_in(sl.psm_spec, in->psm_spec, in_dev, r.p0, np, st, &b.psm_spec, h2d));
-    CK(stage_in(sl.pep_off, in->pep_off, in_dev, r.p0, np + 1, st, &b.pep_off, h2d));
-    CK(stage_in(sl.pep, in->pep, in_dev, pep_lo, pep_hi - pep_lo, st, &b.pep, h2d));
-    CK(stage_in(sl.n_mod, in->n_mod, in_dev, r.p0, np, st, &b.n_mod, h2d));
-    CK(stage_in(sl.max_charge, in->max_charge, in_dev, r.p0, np, st, &b.max_charge, h2d));
-    CK(stage_in(sl.aux_off, in->aux_off, in_dev, r.p0, np + 1, st, &b.aux_off, h2d));
-    if (in->aux_off) {
-        CK(stage_in(sl.aux_pos, in->aux_pos, in_dev, aux_lo, aux_hi - aux_lo, st, &b.aux_pos, h2d));
-        CK(stage_in(sl.aux_mass, in->aux_mass, in_dev, aux_lo, aux_hi - aux_lo, st, &b.aux_mass, h2d));
-    } else { b.aux_pos = nullptr; b.aux_mass = nullptr; }
-    CK(stage_in(sl.mod_off, in->mod_off, in_dev, r.p0, np + 1, st, &cs.mod_off_abs, h2d));
     }
     // PSM-indexed views become chunk-relative
     b.psm_spec += r.p0; b.pep_off += r.p0; b.n_mod += r.p0; b.max_charge += r.p0;
@@ -1509,6 +1528,7 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
     // (and pins the staging buffers, starts the threads), the second narrows and is timed, the third does not and is
     // timed, and the faster way (peaks per second of the whole call) is kept.  It needs PA_NARROW_MIN_THREADS to try.
     const int64_t call_peaks = in_dev || chunks.empty() ? 0 : in->spec_off[chunks.back().s1] - in->spec_off[chunks[0].s0];
+    if (!s->host_threads_fixed && s->pool.th.empty()) s->host_threads = host_thread_budget(s->host_cpus);
     const bool narrow_trial = s->narrow_mode < 0 && !in_dev && call_peaks >= (1 << 20) && s->host_threads >= PA_NARROW_MIN_THREADS;
     const bool want_narrow = s->narrow_mode == 1 || (narrow_trial && (s->narrow_state <= 1 || (s->narrow_state == 3 && s->narrow_keep)));
     const bool may_narrow = !in_dev && want_narrow &&
@@ -1516,8 +1536,7 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
     auto nstage = [&](size_t c) -> NarrowStage& { return s->nstage[c % 3]; };
     auto bail = [&](int code) { if (may_narrow) for (int i = 0; i < 3; i++) if (s->nstage[i].busy) { s->pool.wait(); s->nstage[i].busy = false; } cudaDeviceSynchronize(); return code; };
     if (may_narrow) {
-        rc = narrow_begin(s, nstage(0), in, chunks[0]);
-        if (rc == PA_OK) rc = narrow_end(s, nstage(0), in);
+        rc = narrow_begin(s, nstage(0), in, chunks[0]);           // (chunk_front waits for it, after the chunk's other copies)
         if (rc != PA_OK) return bail(rc);
     }
     rc = chunk_front(s, 0, in, in_dev, chunks[0], mod_lo[0], mod_hi[0], chunk_maxp[0], cs[0], in_dev ? &ends_dev[0] : nullptr,
@@ -1529,10 +1548,6 @@ static int score_impl(pa_scorer* s, const pa_batch* in, const pa_results* out, i
             if (check_chunks) {
                 const char* why = prepare_host_chunk(c + 1);
                 if (why) { bail(0); return fail(s, PA_ERR_ARG, "inconsistent batch: %s", why); }
-            }
-            if (may_narrow) {
-                rc = narrow_end(s, nstage(c + 1), in);
-                if (rc != PA_OK) return bail(rc);
             }
             // slot (c+1)&1 was last used by chunk c-1: its stream order keeps buffers safe
             rc = chunk_front(s, (int)((c + 1) & 1), in, in_dev, chunks[c + 1], mod_lo[c + 1], mod_hi[c + 1],
