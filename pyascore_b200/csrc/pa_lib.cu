@@ -927,6 +927,10 @@ static int narrow_begin(pa_scorer* s, NarrowStage& ns, const pa_batch* in, const
     ns.s0 = r.s0; ns.ns = r.s1 - r.s0;
     ns.peak_lo = in->spec_off[r.s0]; ns.npk = in->spec_off[r.s1] - ns.peak_lo;
     if (ns.ns <= 0 || !(s->narrow_mode == 1 || (s->narrow_mode < 0 && ns.npk >= (1 << 19)))) return PA_OK;
+    // the pass runs a chunk ahead of that chunk's consistency check (prepare_host_chunk): it only touches a chunk whose
+    // spectrum offsets ascend -- anything else goes unnarrowed and is refused by the check when its turn comes
+    for (int64_t q = r.s0; q < r.s1; q++)
+        if (in->spec_off[q + 1] < in->spec_off[q]) return PA_OK;
     CK(cudaEventSynchronize(ns.ev));                      // the chunk that used this set three chunks ago has left it
     CK(ensure_pinned_t(ns.h_mz32, ns.h_mz32_cap, (size_t)ns.npk));
     CK(ensure_pinned_t(ns.h_escoff, ns.h_escoff_cap, (size_t)ns.ns));

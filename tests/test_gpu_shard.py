@@ -323,3 +323,22 @@ def test_row_form_binning_large_spectra(monkeypatch):
         res[mode] = s.score_batch(dict(batch))
         s.close()
     assert _same(res["topn"], res["rows"])
+
+
+def test_inconsistent_offsets_with_narrowing_forced(monkeypatch):
+    """the host narrowing pass works a chunk ahead of that chunk's consistency check: a later chunk whose spectrum offsets
+    jump out of the batch and back must be refused (ValueError), not read or written out of bounds by the pass"""
+    monkeypatch.setenv("PA_NARROW", "1")
+    base = synth.make_batch("lowres_phospho", 60000, seed=4)
+    s = _scorer("lowres_phospho")
+    good = s.score_batch(dict(base))
+    assert s.counters()["n_chunks"] >= 3 and s.counters()["n_spec_exact"] >= 0
+    for where in (0.55, 0.9):
+        b = {k: v.copy() for k, v in base.items()}
+        q = int(where * (b["spec_off"].size - 1))
+        b["spec_off"][q] += 10 ** 9
+        with pytest.raises(ValueError):
+            s.score_batch(b)
+    again = s.score_batch(dict(base))           # the scorer is still usable and still right
+    assert _same(good, again)
+    s.close()
